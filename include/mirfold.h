@@ -1,0 +1,154 @@
+/*
+ * mirfold.h -- C ABI of libmirfold.so, the B200-native fold stage for miR-PREFeR.
+ *
+ * The reference has no FFI for this path; its boundary is a subprocess + text parser:
+ *   caller   : subprocess.check_call("RNALfold -L <PRECURSOR_LEN>", stdin=<FASTA chunk>,
+ *              stdout=<file>)                      /root/reference/miR_PREFeR.py:3053, :3064
+ *   consumer : get_structures_next_extendregion()  /root/reference/miR_PREFeR.py:1541-1599
+ *   duplex   : get_maturestar_info()               /root/reference/miR_PREFeR.py:1876-1999
+ * Each entry point below names the reference interface it replaces.  Plain C types only
+ * (pointers + sizes); no torch / C++ types cross this boundary.  Every function returns
+ * MIRFOLD_OK (0) or a negative error code and never aborts the process.  The library has NO
+ * CPU fallback: without a CUDA device mirfold_open() fails with MIRFOLD_ERR_NO_DEVICE.
+ *
+ * Ownership: inputs are borrowed for the duration of the call; results are owned by the
+ * library until mirfold_free_result().  A context is single-caller (one host thread).
+ * Results are deterministic and independent of device count and batch composition.
+ */
+#ifndef MIRFOLD_H
+#define MIRFOLD_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MIRFOLD_OK 0
+#define MIRFOLD_ERR_NO_DEVICE (-1)   /* no usable CUDA device / bad device id          */
+#define MIRFOLD_ERR_CUDA (-2)        /* CUDA runtime error (see mirfold_last_error)     */
+#define MIRFOLD_ERR_ARG (-3)         /* invalid argument                               */
+#define MIRFOLD_ERR_PARAMSET (-4)    /* unknown energy parameter set                   */
+#define MIRFOLD_ERR_BACKTRACK (-5)   /* traceback found no decomposition (the reference
+                                        aborts with "backtrack failed ...")            */
+#define MIRFOLD_ERR_NOMEM (-6)
+
+/* The only parameter set with a runnable oracle: Turner 1999 as compiled into ViennaRNA
+ * 1.8.5, dangles=1, 37 C, tetraloop bonus on (what `RNALfold -L n` uses by default). */
+#define MIRFOLD_PARAMSET_DEFAULT "vienna-1.8.5-d1"
+
+typedef struct mirfold_ctx mirfold_ctx;
+
+/* One printed RNALfold hairpin line: "<ss> (<mfe/100>) <start>".  Replaces one line of the
+ * text that get_structures_next_extendregion() parses (miR_PREFeR.py:1566-1573). */
+typedef struct mirfold_hit {
+    int32_t start;     /* 1-based start printed by RNALfold                       */
+    int32_t len;       /* strlen of the dot-bracket string                        */
+    int32_t mfe_dcal;  /* energy in 0.01 kcal/mol (the printed %6.2f times 100)   */
+    int32_t reserved;
+    uint64_t ss_off;   /* offset of the NUL-terminated dot-bracket in ss_arena    */
+} mirfold_hit;
+
+typedef struct mirfold_stats {
+    double ms_total;      /* host wall time of the call                                  */
+    double ms_h2d;        /* device time: uploads                                        */
+    double ms_fill;       /* device time of the c/fML band fill kernel(s) (CUDA events)  */
+    double ms_f3;         /* f3 scan kernel                                              */
+    double ms_trace;      /* emission plan + traceback + emission/pack kernels           */
+    double ms_d2h;        /* result download                                             */
+    double ms_device;     /* first kernel start -> last kernel end                       */
+    uint64_t nt;          /* nucleotides folded                                          */
+    uint64_t cells;       /* DP cells (i,j) visited, SURVEY.md 8(d) definition           */
+    uint64_t tracebacks;  /* traceback calls                                             */
+    uint64_t kernel_launches;
+    uint64_t h2d_bytes, d2h_bytes;
+    int32_t n_devices;
+    int32_t n_chunks;
+} mirfold_stats;
+
+/* Result of folding `nseq` records.  Hit order inside a record == RNALfold print order. */
+typedef struct mirfold_result {
+    uint32_t nseq;
+    uint32_t reserved;
+    uint64_t nhits;
+    const uint64_t *hit_begin;   /* nseq+1 entries: hits of record r are [hit_begin[r], hit_begin[r+1]) */
+    const mirfold_hit *hits;     /* nhits entries                                                      */
+    const char *ss_arena;        /* dot-bracket strings, NUL-terminated                                */
+    uint64_t ss_bytes;
+    const int32_t *total_mfe_dcal; /* nseq entries: the " (%6.2f)" total line of each record          */
+    mirfold_stats stats;
+} mirfold_result;
+
+/* Replaces: locating/validating the RNALfold executable (check_RNALfold, miR_PREFeR.py:472-498).
+ * device_ids == NULL or n_devices == 0 -> use the current CUDA device only. */
+int mirfold_open(mirfold_ctx **ctx, const int *device_ids, int n_devices, const char *param_set);
+void mirfold_close(mirfold_ctx *ctx);
+
+/* Replaces: one `RNALfold -L span_L` subprocess run over a FASTA chunk (miR_PREFeR.py:3064)
+ * plus the text parse of its hairpin lines (miR_PREFeR.py:1566-1573).
+ *   seqs    : concatenated raw sequence tokens exactly as they appear on the FASTA sequence
+ *             line (any case, DNA or RNA alphabet, IUPAC allowed; conversion to upper-case
+ *             and T->U happens inside, like RNALfold's main()).
+ *   seq_off : nseq+1 offsets into seqs.
+ * With n_devices > 1 the records are sharded by DP work across the devices (no collectives)
+ * and gathered back in input order. */
+int mirfold_fold(mirfold_ctx *ctx, const char *seqs, const uint64_t *seq_off, uint32_t nseq,
+                 int span_L, uint32_t flags, mirfold_result **out);
+
+/* Device-resident variant used for kernel-only timing: the same pipeline, but the raw
+ * sequences/offsets already live in device memory of device 0 of the context and the
+ * results stay in HBM (nothing is downloaded; *out carries only stats, nhits and nseq).
+ * `stream` is a cudaStream_t passed as void* (NULL = the context's own stream). */
+int mirfold_fold_device(mirfold_ctx *ctx, const void *d_seqs, const void *d_seq_off,
+                        const uint64_t *h_seq_off, uint32_t nseq, int span_L, uint32_t flags,
+                        void *stream, mirfold_result **out);
+
+/* Debug/test hook: fill + f3 for ONE sequence and copy the band matrices back in the oracle's
+ * [i][d] layout (row stride W = min(L,n)+6, rows 0..n+1, INF=1000000 where not computed).
+ * c/m must hold (n+2)*W ints, f3 must hold n+4 ints. */
+int mirfold_debug_matrices(mirfold_ctx *ctx, const char *seq, uint32_t n, int span_L, int32_t *c,
+                           int32_t *m, int32_t *f3);
+
+void mirfold_free_result(mirfold_result *res);
+
+const char *mirfold_strerror(int code);
+/* Human-readable detail of the last error raised in this context (CUDA error string etc). */
+const char *mirfold_last_error(const mirfold_ctx *ctx);
+/* "mirfold <version> sm_100a <paramset>" */
+const char *mirfold_version(void);
+
+/* ---- stage 3: miRNA/miRNA* duplex checks fused on-device (miR_PREFeR.py:1876-1999) ---- */
+
+/* One (structure, mature) query.  Coordinates follow get_maturestar_info()'s arguments. */
+typedef struct mirfold_duplex_query {
+    uint64_t ss_off;       /* dot-bracket string in the arena given to mirfold_duplex()   */
+    int32_t ss_len;
+    int32_t fold_start;    /* 1-based offset of ss[0] in the folded sequence ("foldstart") */
+    int32_t mature_start;  /* genome coords [m0, m1) of the mature candidate               */
+    int32_t mature_end;
+    int32_t region_start;  /* extended region [rs, re)                                     */
+    int32_t region_end;
+    int32_t strand;        /* '+' or '-'                                                   */
+    int32_t reserved;
+} mirfold_duplex_query;
+
+/* Verdict codes: 0 = pass; otherwise index into mirfold_duplex_fail_name(). */
+typedef struct mirfold_duplex_verdict {
+    int32_t code;
+    int32_t star_start, star_end;   /* genome coords of the star                      */
+    int32_t fold_start, fold_end;   /* genome coords of the folded region             */
+    int32_t star_ss_begin, star_ss_end;     /* local slice [b,e) of ss = star_ss      */
+    int32_t mature_ss_begin, mature_ss_end; /* local slice of ss = mature_ss          */
+    int32_t prime5;                 /* 1 if the mature is on the 5' arm               */
+    int32_t total_dots, total_bps;
+} mirfold_duplex_verdict;
+
+int mirfold_duplex(mirfold_ctx *ctx, const char *ss_arena, uint64_t ss_bytes,
+                   const mirfold_duplex_query *queries, uint64_t nq,
+                   mirfold_duplex_verdict *verdicts /* nq entries, caller-allocated */);
+const char *mirfold_duplex_fail_name(int code);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MIRFOLD_H */

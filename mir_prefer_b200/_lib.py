@@ -1,0 +1,96 @@
+"""ctypes binding of libmirfold.so (include/mirfold.h).  No fallback: import fails loudly if the
+CUDA library has not been built (python __graft_entry__.py build, or make -C mir_prefer_b200/csrc)."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmirfold.so")
+
+
+class MirfoldError(RuntimeError):
+    def __init__(self, code, detail=""):
+        self.code = code
+        msg = "libmirfold error %d" % code
+        if detail:
+            msg += ": " + detail
+        super().__init__(msg)
+
+
+class Hit(C.Structure):
+    _fields_ = [("start", C.c_int32), ("len", C.c_int32), ("mfe_dcal", C.c_int32), ("reserved", C.c_int32),
+                ("ss_off", C.c_uint64)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("ms_total", C.c_double), ("ms_h2d", C.c_double), ("ms_fill", C.c_double), ("ms_f3", C.c_double),
+                ("ms_trace", C.c_double), ("ms_d2h", C.c_double), ("ms_device", C.c_double),
+                ("nt", C.c_uint64), ("cells", C.c_uint64), ("tracebacks", C.c_uint64), ("kernel_launches", C.c_uint64),
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("n_devices", C.c_int32), ("n_chunks", C.c_int32)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class Result(C.Structure):
+    _fields_ = [("nseq", C.c_uint32), ("reserved", C.c_uint32), ("nhits", C.c_uint64),
+                ("hit_begin", C.POINTER(C.c_uint64)), ("hits", C.POINTER(Hit)), ("ss_arena", C.c_void_p),
+                ("ss_bytes", C.c_uint64), ("total_mfe_dcal", C.POINTER(C.c_int32)), ("stats", Stats)]
+
+
+class DuplexQuery(C.Structure):
+    _fields_ = [("ss_off", C.c_uint64), ("ss_len", C.c_int32), ("fold_start", C.c_int32),
+                ("mature_start", C.c_int32), ("mature_end", C.c_int32), ("region_start", C.c_int32),
+                ("region_end", C.c_int32), ("strand", C.c_int32), ("reserved", C.c_int32)]
+
+
+class DuplexVerdict(C.Structure):
+    _fields_ = [("code", C.c_int32), ("star_start", C.c_int32), ("star_end", C.c_int32), ("fold_start", C.c_int32),
+                ("fold_end", C.c_int32), ("star_ss_begin", C.c_int32), ("star_ss_end", C.c_int32),
+                ("mature_ss_begin", C.c_int32), ("mature_ss_end", C.c_int32), ("prime5", C.c_int32),
+                ("total_dots", C.c_int32), ("total_bps", C.c_int32)]
+
+
+# every symbol include/mirfold.h declares
+EXPORTS = ["mirfold_open", "mirfold_close", "mirfold_fold", "mirfold_fold_device", "mirfold_debug_matrices",
+           "mirfold_free_result", "mirfold_strerror", "mirfold_last_error", "mirfold_version", "mirfold_duplex",
+           "mirfold_duplex_fail_name"]
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("libmirfold.so is not built (%s). Run `python __graft_entry__.py` or "
+                          "`make -C mir_prefer_b200/csrc`. There is no CPU fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    lib.mirfold_open.argtypes = [C.POINTER(vp), C.POINTER(C.c_int), C.c_int, C.c_char_p]
+    lib.mirfold_open.restype = C.c_int
+    lib.mirfold_close.argtypes = [vp]
+    lib.mirfold_close.restype = None
+    lib.mirfold_fold.argtypes = [vp, C.c_void_p, C.POINTER(C.c_uint64), C.c_uint32, C.c_int, C.c_uint32,
+                                 C.POINTER(C.POINTER(Result))]
+    lib.mirfold_fold.restype = C.c_int
+    lib.mirfold_fold_device.argtypes = [vp, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.c_uint32, C.c_int,
+                                        C.c_uint32, C.c_void_p, C.POINTER(C.POINTER(Result))]
+    lib.mirfold_fold_device.restype = C.c_int
+    lib.mirfold_debug_matrices.argtypes = [vp, C.c_char_p, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.mirfold_debug_matrices.restype = C.c_int
+    lib.mirfold_free_result.argtypes = [C.POINTER(Result)]
+    lib.mirfold_free_result.restype = None
+    lib.mirfold_strerror.argtypes = [C.c_int]
+    lib.mirfold_strerror.restype = C.c_char_p
+    lib.mirfold_last_error.argtypes = [vp]
+    lib.mirfold_last_error.restype = C.c_char_p
+    lib.mirfold_version.argtypes = []
+    lib.mirfold_version.restype = C.c_char_p
+    lib.mirfold_duplex.argtypes = [vp, C.c_void_p, C.c_uint64, C.POINTER(DuplexQuery), C.c_uint64,
+                                   C.POINTER(DuplexVerdict)]
+    lib.mirfold_duplex.restype = C.c_int
+    lib.mirfold_duplex_fail_name.argtypes = [C.c_int]
+    lib.mirfold_duplex_fail_name.restype = C.c_char_p
+    _lib = lib
+    return lib

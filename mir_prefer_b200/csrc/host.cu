@@ -1,0 +1,766 @@
+// host.cu -- libmirfold host runtime: contexts, memory pools, chunked pipeline, multi-GPU sharding
+// and the C ABI declared in include/mirfold.h.
+//
+// Replaces fold_use_RNALfold()/fold() (/root/reference/miR_PREFeR.py:3047-3119): where the reference
+// forks one RNALfold process per FASTA shard, this runtime shards records over GPUs by DP work
+// (no collectives: loci are independent), runs K1..K4 per chunk on one stream per device, and
+// gathers hit records back in input order.  There is no CPU fallback.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include <cub/device/device_scan.cuh>
+
+#include "../../include/mirfold.h"
+#include "mirfold_internal.cuh"
+#include "turner99_v185_tables.inc"
+
+#define MIRFOLD_VERSION "0.1.0"
+
+namespace {
+
+struct DBuf {  // grow-only device buffer
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { e = cudaMalloc(&p, bytes); want = bytes; }
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return (T *)p; }
+};
+
+struct HBuf {  // grow-only pinned host buffer
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return (T *)p; }
+};
+
+struct Partial {  // what one device produced for its share of the records
+    std::vector<uint32_t> recs;            // record ids handled (n >= 5 only)
+    std::vector<uint64_t> rec_hit_begin;   // per handled record: first hit in `hits`
+    std::vector<uint32_t> rec_hit_count;
+    std::vector<int32_t> rec_total;
+    std::vector<mirfold_hit> hits;         // ss_off relative to arena
+    HBuf arena;                            // pinned
+    uint64_t arena_bytes = 0;
+    mirfold_stats st{};
+    int err = MIRFOLD_OK;
+    std::string errmsg;
+};
+
+struct Device {
+    int id = 0;
+    cudaStream_t stream = nullptr;
+    DevParams *dP = nullptr;
+    size_t mem_budget = 0;
+    // pooled buffers
+    DBuf raw, loci, codes, F, C, M, ring, tbcount, tbbase, listoff, startlist, scan_in, scan_out, scan_tmp;
+    DBuf slots, tblen, tbstart, tblocus, tbflag, tbenergy, stackscr, fail, ssoff, hitidx;
+    DBuf o_start, o_len, o_energy, o_ssoff, o_arena;
+    HBuf h_raw, h_loci, h_listoff, h_small, h_out;
+    cudaEvent_t ev[12] = {};
+    void release()
+    {
+        DBuf *all[] = {&raw, &loci, &codes, &F, &C, &M, &ring, &tbcount, &tbbase, &listoff, &startlist, &scan_in,
+                       &scan_out, &scan_tmp, &slots, &tblen, &tbstart, &tblocus, &tbflag, &tbenergy, &stackscr, &fail,
+                       &ssoff, &hitidx, &o_start, &o_len, &o_energy, &o_ssoff, &o_arena};
+        for (DBuf *b : all) b->release();
+        HBuf *hall[] = {&h_raw, &h_loci, &h_listoff, &h_small, &h_out};
+        for (HBuf *b : hall) b->release();
+        for (auto &e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
+        if (dP) cudaFree(dP);
+        dP = nullptr;
+        if (stream) cudaStreamDestroy(stream);
+        stream = nullptr;
+    }
+};
+
+}  // namespace
+
+struct mirfold_ctx {
+    std::vector<Device> devs;
+    std::string last_error;
+    std::vector<HBuf> arena_pool;  // pinned arenas returned by mirfold_free_result
+    std::mutex pool_mu;
+};
+
+namespace {
+
+struct ResultOwner {  // lives right behind the public struct
+    mirfold_result pub;
+    mirfold_ctx *ctx;
+    std::vector<uint64_t> hit_begin;
+    std::vector<mirfold_hit> hits;
+    std::vector<int32_t> totals;
+    HBuf arena;               // single-device fast path: pinned arena moved from the Partial
+    std::vector<char> arena_v;  // multi-device path: concatenated
+};
+
+// ------------------------------------------------------------------ parameter set (a10)
+void build_params(DevParams &P)
+{
+    memset(&P, 0, sizeof P);
+    for (int s = 0; s <= MF_MAX_SPAN + 1; s++) {
+        if (s <= 30) P.hairpinE[s] = T99_hairpin37[s];
+        else P.hairpinE[s] = T99_hairpin37[30] + (int)(T99_lxc37 * log(s / 30.));
+    }
+    for (int k = 0; k < 31; k++) { P.bulge[k] = T99_bulge37[k]; P.internal_loop[k] = T99_internal_loop37[k]; }
+    for (int k = 0; k < 64; k++) { P.stack[k] = T99_stack37[k]; P.pair[k] = (unsigned char)T99_BP_pair[k]; }
+    for (int k = 0; k < 200; k++) { P.mismatchI[k] = T99_mismatchI37[k]; P.mismatchH[k] = T99_mismatchH37[k]; }
+    for (int k = 0; k < 40; k++) {  // dangles are clamped to <= 0 by scale_parameters
+        P.dangle5[k] = std::min(0, T99_dangle5_37[k]);
+        P.dangle3[k] = std::min(0, T99_dangle3_37[k]);
+    }
+    for (int t = 0; t < 8; t++) {
+        P.MLintern[t] = T99_ML_intern37 + (t > 2 ? T99_TerminalAU : 0);
+        P.rtype[t] = (unsigned char)T99_rtype[t];
+    }
+    memcpy(P.int11, T99_int11_37, sizeof P.int11);
+    memcpy(P.int21, T99_int21_37, sizeof P.int21);
+    memcpy(P.int22, T99_int22_37, sizeof P.int22);
+    P.MLclosing = T99_ML_closing37;
+    P.TerminalAU = T99_TerminalAU;
+    // tetraloop bonus by packed 6-mer (first listed entry wins, like strstr)
+    for (int k = T99_N_TETRALOOPS - 1; k >= 0; k--) {
+        int code = 0;
+        bool ok = true;
+        for (int c = 0; c < 6; c++) {
+            const char ch = T99_Tetraloops[7 * k + c];
+            int b = ch == 'A' ? 0 : ch == 'C' ? 1 : ch == 'G' ? 2 : ch == 'U' ? 3 : -1;
+            if (b < 0) ok = false;
+            code |= (b & 3) << (2 * c);
+        }
+        if (ok) P.tetra[code] = (short)T99_TETRA_ENERGY37[k];
+    }
+    // generic interior-loop constants: iteration it pairs loop sizes s=it and s=30-it in one warp
+    const int ninio = T99_F_ninio37[2], maxninio = T99_MAX_NINIO;
+    for (int it = 0; it < 16; it++)
+        for (int lane = 0; lane < 32; lane++) {
+            int s, u;
+            if (it < 15) { if (lane <= it) { s = it; u = lane; } else { s = 30 - it; u = lane - it - 1; } }
+            else { s = 15; u = lane; }
+            const int v = s - u;
+            int val = MF_INF;
+            if (u >= 0 && v >= 0 && u <= s) {
+                const bool special = (u == 0 || v == 0 || (u <= 2 && v <= 2));
+                if (!special) val = T99_internal_loop37[s] + std::min(maxninio, std::abs(u - v) * ninio);
+            }
+            P.ilc[it][lane] = val;
+        }
+    int m = 0;
+    for (int u = 0; u <= 30; u++)
+        for (int v = 0; v <= 30 - u; v++) { P.uv[m][0] = (unsigned char)u; P.uv[m][1] = (unsigned char)v; m++; }
+}
+
+uint64_t cells_of(int n, int L)
+{   // sum_{i=1}^{n-4} (min(n, i+L*) - i - 3)
+    const int Ls = std::min(L, n);
+    uint64_t tot = 0;
+    if (n < 5) return 0;
+    // rows with i+Ls <= n contribute Ls-3, the rest n-i-3
+    const int full = std::max(0, std::min(n - 4, n - Ls));
+    tot += (uint64_t)full * (uint64_t)(Ls - 3);
+    for (int i = full + 1; i <= n - 4; i++) tot += (uint64_t)(n - i - 3);
+    return tot;
+}
+
+#define CK(call)                                                                                 \
+    do {                                                                                         \
+        cudaError_t e_ = (call);                                                                 \
+        if (e_ != cudaSuccess) {                                                                 \
+            out.err = MIRFOLD_ERR_CUDA;                                                          \
+            out.errmsg = std::string(#call) + ": " + cudaGetErrorString(e_);                     \
+            return;                                                                              \
+        }                                                                                        \
+    } while (0)
+
+__global__ void k_widen_counts(const int *__restrict__ in, unsigned long long *__restrict__ out, int n)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k <= n) out[k] = k < n ? (unsigned long long)in[k] : 0ULL;
+}
+__global__ void k_emit_sizes(const int *__restrict__ flag, const int *__restrict__ len,
+                             unsigned long long *__restrict__ bytes, unsigned long long *__restrict__ ones,
+                             unsigned long long ntb)
+{
+    const unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k <= ntb) {
+        const bool f = k < ntb && flag[k];
+        bytes[k] = f ? (unsigned long long)len[k] + 1ULL : 0ULL;
+        ones[k] = f ? 1ULL : 0ULL;
+    }
+}
+
+__global__ void k_gather_bounds(const unsigned long long *tb_base, const unsigned long long *hitidx,
+                                unsigned long long *out, int nl)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k <= nl) out[k] = hitidx[tb_base[k]];
+}
+__global__ void k_gather_totals(const LocusDesc *loci, const int *F, int *out, int nl)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < nl) out[k] = F[loci[k].seq_off + 1];
+}
+
+cudaError_t exclusive_scan(Device &D, const unsigned long long *in, unsigned long long *out, size_t n)
+{
+    size_t tmp = 0;
+    cudaError_t e = cub::DeviceScan::ExclusiveSum(nullptr, tmp, in, out, n, D.stream);
+    if (e != cudaSuccess) return e;
+    e = D.scan_tmp.ensure(tmp);
+    if (e != cudaSuccess) return e;
+    return cub::DeviceScan::ExclusiveSum(D.scan_tmp.p, tmp, in, out, n, D.stream);
+}
+
+struct Locus {
+    uint32_t rec;
+    int n;
+    uint64_t cells;
+};
+
+// Runs the full pipeline for `recs` on one device.  If d_raw != nullptr the raw sequences already
+// live on the device (offsets h_off are into that buffer) and no results are downloaded.
+void run_device(Device &D, const char *seqs, const uint64_t *h_off, const std::vector<uint32_t> &recs, int L,
+                const char *d_raw, bool download, cudaStream_t user_stream, Partial &out)
+{
+    out.st = mirfold_stats{};
+    out.st.n_devices = 1;
+    CK(cudaSetDevice(D.id));
+    cudaStream_t st = user_stream ? user_stream : D.stream;
+    const auto t0 = std::chrono::steady_clock::now();
+
+    std::vector<Locus> loci;
+    loci.reserve(recs.size());
+    for (uint32_t r : recs) {
+        const uint64_t len = h_off[r + 1] - h_off[r];
+        if (len >= 5) {
+            Locus l{r, (int)len, cells_of((int)len, L)};
+            loci.push_back(l);
+            out.st.nt += len;
+            out.st.cells += l.cells;
+        } else out.st.nt += len;
+    }
+    // largest first: the hardware CTA scheduler then behaves like LPT list scheduling
+    std::stable_sort(loci.begin(), loci.end(), [](const Locus &a, const Locus &b) { return a.cells > b.cells; });
+
+    out.recs.clear(); out.rec_hit_begin.clear(); out.rec_hit_count.clear(); out.rec_total.clear(); out.hits.clear();
+    out.arena_bytes = 0;
+
+    // ---- chunking by device memory budget
+    struct Chunk { size_t begin, end; };
+    std::vector<Chunk> chunks;
+    auto locus_bytes = [&](const Locus &l) {
+        const int Ls = std::min(L, l.n), dmax = std::min(Ls, l.n - 1);
+        return (size_t)band_cells(l.n, dmax) * 8 + (size_t)l.n * (MF_RING_PER_NT * 4 + 5 + 2 * 4) + 4096;
+    };
+    {
+        size_t b = 0, acc = 0;
+        for (size_t k = 0; k < loci.size(); k++) {
+            const size_t lb = locus_bytes(loci[k]);
+            if (k > b && acc + lb > D.mem_budget) { chunks.push_back({b, k}); b = k; acc = 0; }
+            acc += lb;
+        }
+        if (b < loci.size()) chunks.push_back({b, loci.size()});
+    }
+    out.st.n_chunks = (int32_t)chunks.size();
+
+    struct ChunkOut {  // device-resident results of a chunk, downloaded at the end
+        uint64_t nhits, arena_bytes;
+    };
+    std::vector<mirfold_hit> &hits = out.hits;
+    // pass 1 over chunks computes everything and downloads the small per-hit arrays + arena
+    // into the pinned arena (grown as needed; chunks are few).
+    std::vector<char> arena_tmp;  // only used when more than one chunk
+    for (size_t ci = 0; ci < chunks.size(); ci++) {
+        const size_t cb = chunks[ci].begin, ce = chunks[ci].end;
+        const int nl = (int)(ce - cb);
+        // ---- descriptors
+        CK(D.h_loci.ensure(sizeof(LocusDesc) * nl));
+        CK(D.h_listoff.ensure(sizeof(unsigned long long) * nl));
+        LocusDesc *hl = D.h_loci.as<LocusDesc>();
+        unsigned long long *hlo = D.h_listoff.as<unsigned long long>();
+        unsigned long long seq_acc = 0, band_acc = 0, ring_acc = 0, raw_acc = 0, list_acc = 0;
+        int max_n = 0, max_Ls = 0;
+        for (int k = 0; k < nl; k++) {
+            const Locus &l = loci[cb + k];
+            LocusDesc &d = hl[k];
+            d.n = l.n; d.Ls = std::min(L, l.n); d.dmax = std::min(d.Ls, l.n - 1); d.rec = (int)l.rec;
+            d.seq_off = seq_acc; d.band_off = band_acc; d.ring_off = ring_acc;
+            d.raw_off = d_raw ? h_off[l.rec] : raw_acc;
+            hlo[k] = list_acc;
+            seq_acc += (unsigned long long)l.n + 3;
+            band_acc += band_cells(l.n, d.dmax);
+            ring_acc += (unsigned long long)l.n * MF_RING_PER_NT;
+            raw_acc += (unsigned long long)l.n;
+            list_acc += (unsigned long long)l.n / 2 + 2;
+            max_n = std::max(max_n, l.n); max_Ls = std::max(max_Ls, d.Ls);
+        }
+        // ---- upload
+        CK(cudaEventRecord(D.ev[0], st));
+        const char *raw_dev = d_raw;
+        if (!d_raw) {
+            CK(D.h_raw.ensure(raw_acc));
+            char *hr = D.h_raw.as<char>();
+            for (int k = 0; k < nl; k++) memcpy(hr + hl[k].raw_off, seqs + h_off[loci[cb + k].rec], (size_t)hl[k].n);
+            CK(D.raw.ensure(raw_acc));
+            CK(cudaMemcpyAsync(D.raw.p, hr, raw_acc, cudaMemcpyHostToDevice, st));
+            out.st.h2d_bytes += raw_acc;
+            raw_dev = D.raw.as<char>();
+        }
+        CK(D.loci.ensure(sizeof(LocusDesc) * nl));
+        CK(cudaMemcpyAsync(D.loci.p, hl, sizeof(LocusDesc) * nl, cudaMemcpyHostToDevice, st));
+        CK(D.listoff.ensure(sizeof(unsigned long long) * nl));
+        CK(cudaMemcpyAsync(D.listoff.p, hlo, sizeof(unsigned long long) * nl, cudaMemcpyHostToDevice, st));
+        out.st.h2d_bytes += (sizeof(LocusDesc) + 8) * (uint64_t)nl;
+        CK(D.codes.ensure(seq_acc));
+        CK(D.F.ensure(seq_acc * 4));
+        CK(D.C.ensure(band_acc * 4));
+        CK(D.M.ensure(band_acc * 4));
+        CK(D.ring.ensure(ring_acc * 4));
+        CK(D.tbcount.ensure((size_t)nl * 4));
+        CK(D.tbbase.ensure((size_t)(nl + 1) * 8));
+        CK(D.scan_in.ensure((size_t)(nl + 1) * 8));
+        CK(D.startlist.ensure(list_acc * 4));
+        CK(D.fail.ensure(4));
+        CK(cudaMemsetAsync(D.fail.p, 0, 4, st));
+        CK(cudaEventRecord(D.ev[1], st));
+        // ---- K1..K3
+        const LocusDesc *dl = D.loci.as<LocusDesc>();
+        CK(launch_prepare(raw_dev, dl, nl, seq_acc, D.codes.as<unsigned char>(), D.F.as<int>(), st));
+        CK(cudaEventRecord(D.ev[2], st));
+        FillLaunch fa{dl, nl, max_n, D.codes.as<unsigned char>(), D.C.as<int>(), D.M.as<int>(), D.ring.as<int>(), D.dP};
+        CK(launch_fill(fa, st));
+        CK(cudaEventRecord(D.ev[3], st));
+        CK(launch_f3(dl, nl, D.codes.as<unsigned char>(), D.C.as<int>(), D.F.as<int>(), D.dP, st));
+        CK(cudaEventRecord(D.ev[4], st));
+        // ---- K4: plan
+        TraceBuffers tb{};
+        tb.loci = dl; tb.nloci = nl; tb.codes = D.codes.as<unsigned char>();
+        tb.C = D.C.as<int>(); tb.M = D.M.as<int>(); tb.F = D.F.as<int>(); tb.P = D.dP;
+        tb.tb_count = D.tbcount.as<int>(); tb.tb_base = D.tbbase.as<unsigned long long>();
+        tb.list_off = D.listoff.as<unsigned long long>(); tb.tb_start_list = D.startlist.as<int>();
+        tb.fail_flag = D.fail.as<int>();
+        CK(launch_plan(tb, st));
+        k_widen_counts<<<(nl + 1 + 255) / 256, 256, 0, st>>>(tb.tb_count, D.scan_in.as<unsigned long long>(), nl);
+        CK(cudaGetLastError());
+        CK(exclusive_scan(D, D.scan_in.as<unsigned long long>(), tb.tb_base, (size_t)nl + 1));
+        CK(D.h_small.ensure(256));
+        unsigned long long *hs = D.h_small.as<unsigned long long>();
+        CK(cudaMemcpyAsync(&hs[0], tb.tb_base + nl, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        const unsigned long long ntb = hs[0];
+        out.st.tracebacks += ntb;
+        out.st.kernel_launches += 6;
+        // ---- traceback
+        tb.ntb = ntb;
+        tb.slot_stride = (max_Ls + 4 + 3) & ~3;
+        tb.stack_cap = max_Ls / 4 + 16;
+        CK(D.slots.ensure((size_t)ntb * tb.slot_stride + 16));
+        CK(D.tblen.ensure((size_t)ntb * 4 + 16)); CK(D.tbstart.ensure((size_t)ntb * 4 + 16));
+        CK(D.tblocus.ensure((size_t)ntb * 4 + 16)); CK(D.tbflag.ensure((size_t)ntb * 4 + 16));
+        CK(D.tbenergy.ensure((size_t)ntb * 4 + 16));
+        CK(D.stackscr.ensure((size_t)ntb * tb.stack_cap * 8 + 16));
+        CK(D.ssoff.ensure((size_t)(ntb + 1) * 8)); CK(D.hitidx.ensure((size_t)(ntb + 1) * 8));
+        CK(D.scan_in.ensure((size_t)(ntb + 1) * 8 + (size_t)(nl + 1) * 8));
+        CK(D.scan_out.ensure((size_t)(ntb + 1) * 8));
+        tb.slots = D.slots.as<char>(); tb.tb_len = D.tblen.as<int>(); tb.tb_start = D.tbstart.as<int>();
+        tb.tb_locus = D.tblocus.as<int>(); tb.tb_flag = D.tbflag.as<int>(); tb.tb_energy = D.tbenergy.as<int>();
+        tb.stack_scratch = D.stackscr.as<int>();
+        CK(launch_traceback(tb, st));
+        CK(launch_emit(tb, st));
+        unsigned long long nhits = 0, abytes = 0;
+        if (ntb) {
+            k_emit_sizes<<<(unsigned)((ntb + 1 + 255) / 256), 256, 0, st>>>(tb.tb_flag, tb.tb_len, D.scan_in.as<unsigned long long>(),
+                                                                             D.scan_out.as<unsigned long long>(), ntb);
+            CK(cudaGetLastError());
+            CK(exclusive_scan(D, D.scan_in.as<unsigned long long>(), D.ssoff.as<unsigned long long>(), (size_t)ntb + 1));
+            CK(exclusive_scan(D, D.scan_out.as<unsigned long long>(), D.hitidx.as<unsigned long long>(), (size_t)ntb + 1));
+            CK(cudaMemcpyAsync(&hs[1], D.ssoff.as<unsigned long long>() + ntb, 8, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(&hs[2], D.hitidx.as<unsigned long long>() + ntb, 8, cudaMemcpyDeviceToHost, st));
+            out.st.kernel_launches += 7;
+        }
+        CK(cudaMemcpyAsync(&hs[3], D.fail.p, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (*(int *)&hs[3]) { out.err = MIRFOLD_ERR_BACKTRACK; out.errmsg = "traceback found no decomposition"; return; }
+        if (ntb) { abytes = hs[1]; nhits = hs[2]; }
+        CK(D.o_start.ensure(nhits * 4 + 16)); CK(D.o_len.ensure(nhits * 4 + 16)); CK(D.o_energy.ensure(nhits * 4 + 16));
+        CK(D.o_ssoff.ensure(nhits * 8 + 16)); CK(D.o_arena.ensure(abytes + 16));
+        CK(launch_pack(tb, D.ssoff.as<unsigned long long>(), D.hitidx.as<unsigned long long>(), D.o_arena.as<char>(),
+                       D.o_start.as<int>(), D.o_len.as<int>(), D.o_energy.as<int>(), D.o_ssoff.as<unsigned long long>(), st));
+        out.st.kernel_launches += 1;
+        CK(cudaEventRecord(D.ev[5], st));
+        // ---- download
+        const size_t small_bytes = (size_t)nhits * (4 + 4 + 4 + 8) + (size_t)(nl + 1) * 8 * 2 + seq_acc * 0 + 64;
+        if (download) {
+            // per-locus first-hit index = hitidx[tb_base[l]] -> gather on host from two small arrays
+            CK(D.h_out.ensure(small_bytes + (size_t)ntb * 0 + (size_t)nl * 4 + 64));
+            char *ho = D.h_out.as<char>();
+            int *h_start = (int *)ho;
+            int *h_len = h_start + nhits;
+            int *h_energy = h_len + nhits;
+            unsigned long long *h_ssoff = (unsigned long long *)(((uintptr_t)(h_energy + nhits) + 7) & ~(uintptr_t)7);
+            unsigned long long *h_tbbase = h_ssoff + nhits;
+            int *h_total = (int *)(h_tbbase + nl + 1);
+            if (nhits) {
+                CK(cudaMemcpyAsync(h_start, D.o_start.p, nhits * 4, cudaMemcpyDeviceToHost, st));
+                CK(cudaMemcpyAsync(h_len, D.o_len.p, nhits * 4, cudaMemcpyDeviceToHost, st));
+                CK(cudaMemcpyAsync(h_energy, D.o_energy.p, nhits * 4, cudaMemcpyDeviceToHost, st));
+                CK(cudaMemcpyAsync(h_ssoff, D.o_ssoff.p, nhits * 8, cudaMemcpyDeviceToHost, st));
+            }
+            // hit index at each locus boundary: hitidx[tb_base[l]] (device gather -> reuse scan_in)
+            {
+                // gather kernel inline via thrust-free lambda: small kernel below
+                k_gather_bounds<<<(nl + 1 + 255) / 256, 256, 0, st>>>(tb.tb_base, D.hitidx.as<unsigned long long>(),
+                                                                      D.scan_in.as<unsigned long long>(), nl);
+                CK(cudaGetLastError());
+                out.st.kernel_launches += 1;
+                CK(cudaMemcpyAsync(h_tbbase, D.scan_in.p, (size_t)(nl + 1) * 8, cudaMemcpyDeviceToHost, st));
+            }
+            // totals: F[seq_off + 1] per locus -> strided; copy via 2D memcpy is awkward, use gather kernel
+            {
+                CK(D.tbcount.ensure((size_t)nl * 4));
+                k_gather_totals<<<(nl + 255) / 256, 256, 0, st>>>(dl, D.F.as<int>(), D.tbcount.as<int>(), nl);
+                CK(cudaGetLastError());
+                out.st.kernel_launches += 1;
+                CK(cudaMemcpyAsync(h_total, D.tbcount.p, (size_t)nl * 4, cudaMemcpyDeviceToHost, st));
+            }
+            // arena: straight into the pinned result arena
+            const uint64_t abase = out.arena_bytes;
+            if (chunks.size() == 1) {
+                CK(out.arena.ensure(abytes + 16));
+            } else {
+                // multi-chunk: grow by reallocating pinned memory (rare path)
+                if (out.arena.cap < abase + abytes + 16) {
+                    HBuf bigger;
+                    CK(bigger.ensure((abase + abytes) * 2 + 16));
+                    if (abase) memcpy(bigger.p, out.arena.p, abase);
+                    out.arena.release();
+                    out.arena = bigger;
+                }
+            }
+            if (abytes) CK(cudaMemcpyAsync(out.arena.as<char>() + abase, D.o_arena.p, abytes, cudaMemcpyDeviceToHost, st));
+            CK(cudaEventRecord(D.ev[6], st));
+            CK(cudaStreamSynchronize(st));
+            out.st.d2h_bytes += nhits * 20 + (uint64_t)(nl + 1) * 8 + (uint64_t)nl * 4 + abytes + 32;
+            const uint64_t hbase = hits.size();
+            hits.resize(hbase + nhits);
+            for (uint64_t h = 0; h < nhits; h++) {
+                mirfold_hit &x = hits[hbase + h];
+                x.start = h_start[h]; x.len = h_len[h]; x.mfe_dcal = h_energy[h]; x.reserved = 0;
+                x.ss_off = abase + h_ssoff[h];
+            }
+            for (int k = 0; k < nl; k++) {
+                out.recs.push_back(loci[cb + k].rec);
+                out.rec_hit_begin.push_back(hbase + h_tbbase[k]);
+                out.rec_hit_count.push_back((uint32_t)(h_tbbase[k + 1] - h_tbbase[k]));
+                out.rec_total.push_back(h_total[k]);
+            }
+            out.arena_bytes = abase + abytes;
+        } else {
+            CK(cudaEventRecord(D.ev[6], st));
+            CK(cudaStreamSynchronize(st));
+            out.arena_bytes += abytes;
+            out.st.d2h_bytes += 32;
+            // count only
+            out.rec_hit_begin.push_back(nhits);
+        }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, D.ev[0], D.ev[1]); out.st.ms_h2d += ms;
+        cudaEventElapsedTime(&ms, D.ev[2], D.ev[3]); out.st.ms_fill += ms;
+        cudaEventElapsedTime(&ms, D.ev[3], D.ev[4]); out.st.ms_f3 += ms;
+        cudaEventElapsedTime(&ms, D.ev[4], D.ev[5]); out.st.ms_trace += ms;
+        cudaEventElapsedTime(&ms, D.ev[5], D.ev[6]); out.st.ms_d2h += ms;
+        cudaEventElapsedTime(&ms, D.ev[1], D.ev[5]); out.st.ms_device += ms;
+    }
+    out.st.ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+}
+
+}  // namespace
+
+// ====================================================================================== C ABI
+extern "C" {
+
+const char *mirfold_version(void) { return "mirfold " MIRFOLD_VERSION " sm_100a " MIRFOLD_PARAMSET_DEFAULT; }
+
+const char *mirfold_strerror(int code)
+{
+    switch (code) {
+    case MIRFOLD_OK: return "ok";
+    case MIRFOLD_ERR_NO_DEVICE: return "no usable CUDA device (libmirfold has no CPU fallback)";
+    case MIRFOLD_ERR_CUDA: return "CUDA runtime error";
+    case MIRFOLD_ERR_ARG: return "invalid argument";
+    case MIRFOLD_ERR_PARAMSET: return "unknown energy parameter set";
+    case MIRFOLD_ERR_BACKTRACK: return "backtrack failed";
+    case MIRFOLD_ERR_NOMEM: return "out of memory";
+    default: return "unknown error";
+    }
+}
+
+const char *mirfold_last_error(const mirfold_ctx *ctx) { return ctx ? ctx->last_error.c_str() : ""; }
+
+int mirfold_open(mirfold_ctx **pctx, const int *device_ids, int n_devices, const char *param_set)
+{
+    if (!pctx) return MIRFOLD_ERR_ARG;
+    *pctx = nullptr;
+    if (param_set && strcmp(param_set, MIRFOLD_PARAMSET_DEFAULT) != 0) return MIRFOLD_ERR_PARAMSET;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return MIRFOLD_ERR_NO_DEVICE; }
+    std::vector<int> ids;
+    if (!device_ids || n_devices <= 0) {
+        int cur = 0;
+        if (cudaGetDevice(&cur) != cudaSuccess) return MIRFOLD_ERR_NO_DEVICE;
+        ids.push_back(cur);
+    } else {
+        for (int k = 0; k < n_devices; k++) {
+            if (device_ids[k] < 0 || device_ids[k] >= ndev) return MIRFOLD_ERR_NO_DEVICE;
+            ids.push_back(device_ids[k]);
+        }
+    }
+    mirfold_ctx *ctx = new mirfold_ctx();
+    DevParams *hp = new DevParams();
+    build_params(*hp);
+    int rc = MIRFOLD_OK;
+    for (int id : ids) {
+        Device D;
+        D.id = id;
+        cudaError_t e = cudaSetDevice(id);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&D.stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaMalloc(&D.dP, sizeof(DevParams));
+        if (e == cudaSuccess) e = cudaMemcpy(D.dP, hp, sizeof(DevParams), cudaMemcpyHostToDevice);
+        for (auto &ev : D.ev) if (e == cudaSuccess) e = cudaEventCreate(&ev);
+        size_t fr = 0, tot = 0;
+        if (e == cudaSuccess) e = cudaMemGetInfo(&fr, &tot);
+        if (e != cudaSuccess) { ctx->last_error = cudaGetErrorString(e); rc = MIRFOLD_ERR_CUDA; D.release(); break; }
+        const char *env = getenv("MIRFOLD_MEM_BUDGET_MB");
+        D.mem_budget = env ? (size_t)atoll(env) << 20 : std::min<size_t>((size_t)(fr * 0.55), (size_t)64 << 30);
+        ctx->devs.push_back(D);
+    }
+    delete hp;
+    if (rc != MIRFOLD_OK) { for (auto &D : ctx->devs) D.release(); delete ctx; return rc; }
+    *pctx = ctx;
+    return MIRFOLD_OK;
+}
+
+void mirfold_close(mirfold_ctx *ctx)
+{
+    if (!ctx) return;
+    for (auto &D : ctx->devs) { cudaSetDevice(D.id); D.release(); }
+    for (auto &b : ctx->arena_pool) b.release();
+    delete ctx;
+}
+
+static void add_stats(mirfold_stats &a, const mirfold_stats &b)
+{
+    a.ms_h2d = std::max(a.ms_h2d, b.ms_h2d); a.ms_fill = std::max(a.ms_fill, b.ms_fill);
+    a.ms_f3 = std::max(a.ms_f3, b.ms_f3); a.ms_trace = std::max(a.ms_trace, b.ms_trace);
+    a.ms_d2h = std::max(a.ms_d2h, b.ms_d2h); a.ms_device = std::max(a.ms_device, b.ms_device);
+    a.nt += b.nt; a.cells += b.cells; a.tracebacks += b.tracebacks; a.kernel_launches += b.kernel_launches;
+    a.h2d_bytes += b.h2d_bytes; a.d2h_bytes += b.d2h_bytes; a.n_chunks += b.n_chunks;
+}
+
+static int fold_impl(mirfold_ctx *ctx, const char *seqs, const uint64_t *seq_off, uint32_t nseq, int span_L,
+                     const char *d_raw, bool download, void *stream, mirfold_result **out)
+{
+    if (!ctx || !out || !seq_off || (!seqs && !d_raw && nseq)) return MIRFOLD_ERR_ARG;
+    if (span_L < 5 || span_L > MF_MAX_SPAN) { ctx->last_error = "span_L out of range [5, 4096]"; return MIRFOLD_ERR_ARG; }
+    *out = nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
+    const int G = d_raw ? 1 : (int)ctx->devs.size();
+    // ---- shard records over devices: greedy LPT on DP cells; no collectives
+    std::vector<std::vector<uint32_t>> shard(G);
+    if (G == 1) {
+        shard[0].resize(nseq);
+        for (uint32_t r = 0; r < nseq; r++) shard[0][r] = r;
+    } else {
+        std::vector<std::pair<uint64_t, uint32_t>> w(nseq);
+        for (uint32_t r = 0; r < nseq; r++) w[r] = {cells_of((int)(seq_off[r + 1] - seq_off[r]), span_L), r};
+        std::stable_sort(w.begin(), w.end(), [](const auto &a, const auto &b) { return a.first > b.first; });
+        std::vector<uint64_t> load(G, 0);
+        for (auto &x : w) {
+            int g = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+            shard[g].push_back(x.second);
+            load[g] += x.first + 1;
+        }
+        for (auto &s : shard) std::sort(s.begin(), s.end());
+    }
+    std::vector<Partial> parts(G);
+    {
+        std::lock_guard<std::mutex> lk(ctx->pool_mu);
+        for (int g = 0; g < G && !ctx->arena_pool.empty(); g++) { parts[g].arena = ctx->arena_pool.back(); ctx->arena_pool.pop_back(); }
+    }
+    if (G == 1) run_device(ctx->devs[0], seqs, seq_off, shard[0], span_L, d_raw, download, (cudaStream_t)stream, parts[0]);
+    else {
+        std::vector<std::thread> th;
+        for (int g = 0; g < G; g++)
+            th.emplace_back([&, g] { run_device(ctx->devs[g], seqs, seq_off, shard[g], span_L, nullptr, download, nullptr, parts[g]); });
+        for (auto &t : th) t.join();
+    }
+    for (int g = 0; g < G; g++)
+        if (parts[g].err != MIRFOLD_OK) {
+            ctx->last_error = parts[g].errmsg;
+            for (auto &p : parts) p.arena.release();
+            return parts[g].err;
+        }
+    // ---- gather in input order
+    ResultOwner *R = new ResultOwner();
+    R->ctx = ctx;
+    R->hit_begin.assign((size_t)nseq + 1, 0);
+    R->totals.assign(nseq, 0);
+    mirfold_stats st{};
+    uint64_t nhits = 0;
+    if (download) {
+        std::vector<uint32_t> cnt(nseq, 0);
+        std::vector<uint64_t> arena_base(G, 0);
+        uint64_t abytes = 0;
+        for (int g = 0; g < G; g++) { arena_base[g] = abytes; abytes += parts[g].arena_bytes; }
+        for (int g = 0; g < G; g++)
+            for (size_t k = 0; k < parts[g].recs.size(); k++) {
+                cnt[parts[g].recs[k]] = parts[g].rec_hit_count[k];
+                R->totals[parts[g].recs[k]] = parts[g].rec_total[k];
+            }
+        for (uint32_t r = 0; r < nseq; r++) R->hit_begin[r + 1] = R->hit_begin[r] + cnt[r];
+        nhits = R->hit_begin[nseq];
+        R->hits.resize(nhits);
+        for (int g = 0; g < G; g++)
+            for (size_t k = 0; k < parts[g].recs.size(); k++) {
+                const uint32_t r = parts[g].recs[k];
+                const mirfold_hit *src = parts[g].hits.data() + parts[g].rec_hit_begin[k];
+                mirfold_hit *dst = R->hits.data() + R->hit_begin[r];
+                for (uint32_t h = 0; h < parts[g].rec_hit_count[k]; h++) { dst[h] = src[h]; dst[h].ss_off += arena_base[g]; }
+            }
+        if (G == 1) {
+            R->arena = parts[0].arena;  // pinned buffer moves into the result
+            parts[0].arena = HBuf();
+            R->pub.ss_arena = R->arena.as<char>();
+        } else {
+            R->arena_v.resize(abytes + 1);
+            for (int g = 0; g < G; g++) {
+                if (parts[g].arena_bytes) memcpy(R->arena_v.data() + arena_base[g], parts[g].arena.p, parts[g].arena_bytes);
+                std::lock_guard<std::mutex> lk(ctx->pool_mu);
+                ctx->arena_pool.push_back(parts[g].arena);
+                parts[g].arena = HBuf();
+            }
+            R->pub.ss_arena = R->arena_v.data();
+        }
+        R->pub.ss_bytes = abytes;
+    } else {
+        for (int g = 0; g < G; g++) { for (uint64_t v : parts[g].rec_hit_begin) nhits += v; R->pub.ss_bytes += parts[g].arena_bytes; }
+        for (auto &p : parts) if (p.arena.p) { std::lock_guard<std::mutex> lk(ctx->pool_mu); ctx->arena_pool.push_back(p.arena); p.arena = HBuf(); }
+        R->pub.ss_arena = nullptr;
+    }
+    for (int g = 0; g < G; g++) add_stats(st, parts[g].st);
+    st.n_devices = G;
+    st.ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    R->pub.nseq = nseq;
+    R->pub.nhits = nhits;
+    R->pub.hit_begin = R->hit_begin.data();
+    R->pub.hits = R->hits.data();
+    R->pub.total_mfe_dcal = R->totals.data();
+    R->pub.stats = st;
+    *out = &R->pub;
+    return MIRFOLD_OK;
+}
+
+int mirfold_fold(mirfold_ctx *ctx, const char *seqs, const uint64_t *seq_off, uint32_t nseq, int span_L, uint32_t flags,
+                 mirfold_result **out)
+{
+    (void)flags;
+    return fold_impl(ctx, seqs, seq_off, nseq, span_L, nullptr, true, nullptr, out);
+}
+
+int mirfold_fold_device(mirfold_ctx *ctx, const void *d_seqs, const void *d_seq_off, const uint64_t *h_seq_off,
+                        uint32_t nseq, int span_L, uint32_t flags, void *stream, mirfold_result **out)
+{
+    (void)flags; (void)d_seq_off;
+    if (!d_seqs) return MIRFOLD_ERR_ARG;
+    return fold_impl(ctx, nullptr, h_seq_off, nseq, span_L, (const char *)d_seqs, false, stream, out);
+}
+
+void mirfold_free_result(mirfold_result *res)
+{
+    if (!res) return;
+    ResultOwner *R = reinterpret_cast<ResultOwner *>(res);
+    if (R->arena.p && R->ctx) {
+        std::lock_guard<std::mutex> lk(R->ctx->pool_mu);
+        if (R->ctx->arena_pool.size() < 4) { R->ctx->arena_pool.push_back(R->arena); R->arena = HBuf(); }
+    }
+    R->arena.release();
+    delete R;
+}
+
+int mirfold_debug_matrices(mirfold_ctx *ctx, const char *seq, uint32_t n, int span_L, int32_t *c, int32_t *m, int32_t *f3)
+{
+    if (!ctx || !seq || n < 5 || !c || !m || !f3) return MIRFOLD_ERR_ARG;
+    Device &D = ctx->devs[0];
+#undef CK
+#define CK(call)                                                                  \
+    do {                                                                          \
+        cudaError_t e_ = (call);                                                  \
+        if (e_ != cudaSuccess) { ctx->last_error = cudaGetErrorString(e_); return MIRFOLD_ERR_CUDA; } \
+    } while (0)
+    CK(cudaSetDevice(D.id));
+    cudaStream_t st = D.stream;
+    LocusDesc d{};
+    d.n = (int)n; d.Ls = std::min(span_L, (int)n); d.dmax = std::min(d.Ls, (int)n - 1);
+    const unsigned long long cells = band_cells(d.n, d.dmax);
+    CK(D.raw.ensure(n)); CK(D.loci.ensure(sizeof d)); CK(D.codes.ensure(n + 3)); CK(D.F.ensure((n + 3) * 4));
+    CK(D.C.ensure(cells * 4)); CK(D.M.ensure(cells * 4)); CK(D.ring.ensure((size_t)n * MF_RING_PER_NT * 4));
+    CK(cudaMemcpyAsync(D.raw.p, seq, n, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(D.loci.p, &d, sizeof d, cudaMemcpyHostToDevice, st));
+    const LocusDesc *dl = D.loci.as<LocusDesc>();
+    CK(launch_prepare(D.raw.as<char>(), dl, 1, n + 3, D.codes.as<unsigned char>(), D.F.as<int>(), st));
+    FillLaunch fa{dl, 1, (int)n, D.codes.as<unsigned char>(), D.C.as<int>(), D.M.as<int>(), D.ring.as<int>(), D.dP};
+    CK(launch_fill(fa, st));
+    CK(launch_f3(dl, 1, D.codes.as<unsigned char>(), D.C.as<int>(), D.F.as<int>(), D.dP, st));
+    std::vector<int> hc(cells), hm(cells), hf(n + 3);
+    CK(cudaMemcpyAsync(hc.data(), D.C.p, cells * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(hm.data(), D.M.p, cells * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(hf.data(), D.F.p, (n + 3) * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const int W = d.Ls + 6;
+    for (size_t k = 0; k < (size_t)(n + 2) * W; k++) c[k] = m[k] = MF_INF;
+    for (int dd = 4; dd <= d.dmax; dd++)
+        for (int i = 1; i <= (int)n - dd; i++) {
+            c[(size_t)i * W + dd] = hc[band_doff(d.n, dd) + (i - 1)];
+            m[(size_t)i * W + dd] = hm[band_doff(d.n, dd) + (i - 1)];
+        }
+    for (uint32_t k = 0; k < n + 3; k++) f3[k] = hf[k];
+    f3[n + 3] = 0;
+    return MIRFOLD_OK;
+}
+
+int mirfold_duplex(mirfold_ctx *ctx, const char *, uint64_t, const mirfold_duplex_query *, uint64_t, mirfold_duplex_verdict *)
+{
+    if (ctx) ctx->last_error = "mirfold_duplex: not built yet";
+    return MIRFOLD_ERR_ARG;
+}
+const char *mirfold_duplex_fail_name(int) { return ""; }
+
+}  // extern "C"

@@ -1,0 +1,103 @@
+// mirfold_internal.cuh -- shared device/host declarations of libmirfold (not part of the C ABI).
+//
+// Data layout in HBM:
+//   codes : per locus n+3 bytes, index 0..n+2; byte = S | (S1 << 4); S[0]=S[n+1]=S[n+2]=0
+//   F     : per locus n+3 int32 at the same offsets (f3[0..n+2], f3[k>n-4]=0)
+//   C, M  : diagonal-major band per locus: diagonal d (=j-i, 4..dmax) holds cells i=1..n-d
+//           contiguously at band_off + band_doff(n,d) + (i-1).  dmax = min(L*, n-1).
+//           All threads walking one anti-diagonal therefore touch consecutive addresses.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#define MF_INF 1000000
+#define MF_TURN 3
+#define MF_MAXLOOP 30
+#define MF_MAX_SPAN 4096 /* hairpin-size table length; PRECURSOR_LEN is capped at 3000 (MP:168) */
+
+struct DevParams {
+    int hairpinE[MF_MAX_SPAN + 2];  // by loop size, incl. the lxc*log extrapolation (A.2)
+    int bulge[31], internal_loop[31];
+    int stack[64];
+    int mismatchI[200], mismatchH[200];
+    int dangle5[40], dangle3[40];  // clamped <= 0
+    int MLintern[8];
+    int int11[8 * 8 * 25], int21[8 * 8 * 125], int22[8 * 8 * 625];
+    int ilc[16][32];               // generic interior-loop constants per (iteration, lane); INF = masked
+    int MLclosing, TerminalAU;
+    short tetra[4096];             // tetraloop bonus by 2-bit packed 6-mer
+    unsigned char pair[64];        // BP_pair[S_i*8+S_j]
+    unsigned char rtype[8];
+    unsigned char uv[496][2];      // traceback (p,q) candidate order: u ascending, v ascending
+};
+
+struct LocusDesc {
+    unsigned long long seq_off;   // into codes / F (elements)
+    unsigned long long band_off;  // into C / M (elements)
+    unsigned long long ring_off;  // into ring scratch (elements)
+    unsigned long long raw_off;   // into the raw ASCII buffer
+    int n;
+    int Ls;    // L* = min(L, n)
+    int dmax;  // min(Ls, n-1)
+    int rec;   // input record index
+};
+
+__host__ __device__ __forceinline__ unsigned long long band_doff(int n, int d)
+{
+    return (unsigned long long)(d - 4) * (unsigned long long)n -
+           ((unsigned long long)d * (unsigned long long)(d - 1) / 2ULL - 6ULL);
+}
+__host__ __device__ __forceinline__ unsigned long long band_cells(int n, int dmax)
+{
+    return dmax >= 4 ? band_doff(n, dmax + 1) : 0ULL;
+}
+
+#define MF_RING_CM 64  /* Cm window ring (needs >= 33 diagonals) */
+#define MF_RING_DML 16 /* DML ring (needs >= 9 diagonals)        */
+#define MF_RING_PER_NT (MF_RING_CM + MF_RING_DML)
+
+// ---- kernel launchers (each defined next to its kernels) -------------------------------
+struct FillLaunch {
+    const LocusDesc *loci;
+    int nloci;
+    int max_n;
+    const unsigned char *codes;
+    int *C, *M, *ring;
+    const DevParams *P;
+};
+cudaError_t launch_prepare(const char *raw, const LocusDesc *loci, int nloci, unsigned long long total_codes,
+                           unsigned char *codes, int *F, cudaStream_t st);
+cudaError_t launch_fill(const FillLaunch &a, cudaStream_t st);
+cudaError_t launch_f3(const LocusDesc *loci, int nloci, const unsigned char *codes, const int *C, int *F,
+                      const DevParams *P, cudaStream_t st);
+
+struct TraceBuffers {
+    const LocusDesc *loci;
+    int nloci;
+    const unsigned char *codes;
+    const int *C, *M, *F;
+    const DevParams *P;
+    // plan
+    int *tb_count;                 // nloci
+    unsigned long long *tb_base;   // nloci+1 (exclusive scan of tb_count)
+    unsigned long long *list_off;  // nloci : offset of the locus' start list in tb_start_list
+    int *tb_start_list;            // per locus up to n/2+2 starts
+    // per traceback
+    unsigned long long ntb;
+    int slot_stride;               // bytes per structure slot
+    char *slots;                   // ntb * slot_stride
+    int *tb_len;                   // ntb
+    int *tb_start;                 // ntb
+    int *tb_locus;                 // ntb
+    int *tb_flag;                  // ntb : printed?
+    int *tb_energy;                // ntb
+    int *stack_scratch;            // ntb * stack_cap * 2 ints
+    int stack_cap;
+    int *fail_flag;                // 1 int
+};
+cudaError_t launch_plan(const TraceBuffers &b, cudaStream_t st);
+cudaError_t launch_traceback(const TraceBuffers &b, cudaStream_t st);
+cudaError_t launch_emit(const TraceBuffers &b, cudaStream_t st);
+cudaError_t launch_pack(const TraceBuffers &b, const unsigned long long *ss_off, const unsigned long long *hit_idx,
+                        char *arena, int *out_start, int *out_len, int *out_energy, unsigned long long *out_ssoff,
+                        cudaStream_t st);

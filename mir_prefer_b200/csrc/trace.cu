@@ -1,0 +1,416 @@
+// trace.cu -- emission plan, order-exact traceback and hairpin emission (K4) for sm_100a.
+//
+// Replaces RNALfold's emission state machine and backtrack() (spec
+// Appendix A.4-A.5, "RLF Lfold.c:402-435, 459-771").  The reference interleaves tracebacks with
+// the row loop; here the band is complete first, which makes every traceback independent:
+//   k_plan      : the state machine depends on f3 only -> list of traceback starts per locus
+//   k_traceback : one warp per traceback; every "first match wins" scan of the reference is a
+//                 lane-parallel test in reference order + ballot/ffs (lowest lane = first match)
+//   k_emit      : the shifted-strncmp containment test between consecutive tracebacks decides
+//                 which structures RNALfold would have printed; energy = f3[start]-f3[start+len]
+//   k_pack      : compacts printed structures into the result arena (offsets from a device scan)
+#include "mirfold_internal.cuh"
+
+#define FULL 0xffffffffu
+
+// ------------------------------------------------------------------------------------ plan
+__global__ void k_plan(TraceBuffers b)
+{
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= b.nloci) return;
+    const LocusDesc L = b.loci[l];
+    const int *F = b.F + L.seq_off;
+    int *list = b.tb_start_list + b.list_off[l];
+    int cnt = 0, do_bt = 0, have_prev = 0;
+    int fnext = F[L.n - 3];
+    for (int i = L.n - 4; i >= 1; i--) {
+        const int fi = F[i];
+        if (fi != fnext) do_bt = 1;
+        else if (do_bt) { list[cnt++] = i + 1; have_prev = 1; do_bt = 0; }
+        if (i == 1) {
+            if (!have_prev) do_bt = 1;
+            if (do_bt) list[cnt++] = 1;   // final backtrack(1, L*)
+        }
+        fnext = fi;
+    }
+    b.tb_count[l] = cnt;
+}
+
+cudaError_t launch_plan(const TraceBuffers &b, cudaStream_t st)
+{
+    if (b.nloci == 0) return cudaSuccess;
+    k_plan<<<(b.nloci + 127) / 128, 128, 0, st>>>(b);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------ traceback
+struct Fold {
+    const DevParams *__restrict__ P;
+    const unsigned char *__restrict__ cd;  // codes, 1-based
+    const int *__restrict__ C;
+    const int *__restrict__ M;
+    const int *__restrict__ F;
+    int n, Ls;
+    __device__ __forceinline__ int S(int k) const { return cd[k] & 7; }
+    __device__ __forceinline__ int S1(int k) const { return cd[k] >> 4; }
+    __device__ __forceinline__ int type(int i, int j) const
+    {
+        const int d = j - i;
+        if (i < 1 || j > n || d < 4 || d >= Ls) return 0;
+        return P->pair[S(i) * 8 + S(j)];
+    }
+    __device__ __forceinline__ int band(const int *__restrict__ A, int i, int j) const
+    {
+        const int d = j - i;
+        if (i < 1 || j > n || d < 4 || d > Ls) return MF_INF;
+        return A[band_doff(n, d) + (i - 1)];
+    }
+    __device__ __forceinline__ int c(int i, int j) const { return band(C, i, j); }
+    __device__ __forceinline__ int m(int i, int j) const { return band(M, i, j); }
+    __device__ __forceinline__ int f(int i) const { return (i >= 1 && i <= n + 2) ? F[i] : 0; }
+    __device__ __forceinline__ int AU(int t) const { return t > 2 ? P->TerminalAU : 0; }
+};
+
+__device__ int tb_loop_energy(const Fold &f, int i, int j, int p, int q, int t, int t2)
+{
+    const DevParams *__restrict__ P = f.P;
+    const int n1 = p - i - 1, n2 = j - q - 1;
+    const int nl = max(n1, n2), ns = min(n1, n2);
+    if (nl == 0) return P->stack[t * 8 + t2];
+    if (ns == 0) {
+        int e = P->bulge[nl];
+        if (nl == 1) return e + P->stack[t * 8 + t2];
+        return e + f.AU(t) + f.AU(t2);
+    }
+    const int si1 = f.S1(i + 1), sj1 = f.S1(j - 1), sp1 = f.S1(p - 1), sq1 = f.S1(q + 1);
+    if (ns == 1 && nl == 1) return P->int11[((t * 8 + t2) * 5 + si1) * 5 + sj1];
+    if (ns == 1 && nl == 2) {
+        if (n1 == 1) return P->int21[(((t * 8 + t2) * 5 + si1) * 5 + sq1) * 5 + sj1];
+        return P->int21[(((t2 * 8 + t) * 5 + sq1) * 5 + si1) * 5 + sp1];
+    }
+    if (n1 == 2 && n2 == 2) return P->int22[((((t * 8 + t2) * 5 + si1) * 5 + sp1) * 5 + sq1) * 5 + sj1];
+    return P->internal_loop[n1 + n2] + min(300, (nl - ns) * 50) + P->mismatchI[(t * 5 + si1) * 5 + sj1] +
+           P->mismatchI[(t2 * 5 + sq1) * 5 + sp1];
+}
+
+__device__ int tb_hairpin(const Fold &f, int i, int j, int t)
+{
+    const DevParams *__restrict__ P = f.P;
+    const int s = j - i - 1;
+    int e = P->hairpinE[s];
+    if (s == 4) {
+        int code = 0, ok = 1;
+        for (int k = 0; k < 6; k++) {
+            const int b = f.S(i + k);
+            ok &= (b >= 1 && b <= 4);
+            code |= ((b - 1) & 3) << (2 * k);
+        }
+        if (ok) e += P->tetra[code];
+    }
+    if (s == 3) e += f.AU(t);
+    else e += P->mismatchH[(t * 5 + f.S1(i + 1)) * 5 + f.S1(j - 1)];
+    return e;
+}
+
+// one warp per traceback
+__global__ void __launch_bounds__(128) k_traceback(TraceBuffers b)
+{
+    const unsigned long long g = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (g >= b.ntb) return;
+    // locate the locus: largest l with tb_base[l] <= g
+    int lo = 0, hi = b.nloci;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (b.tb_base[mid] <= g) lo = mid; else hi = mid;
+    }
+    const int l = lo;
+    const LocusDesc L = b.loci[l];
+    const int kidx = (int)(g - b.tb_base[l]);
+    const int start = b.tb_start_list[b.list_off[l] + kidx];
+    Fold f;
+    f.P = b.P; f.cd = b.codes + L.seq_off; f.C = b.C + L.band_off; f.M = b.M + L.band_off; f.F = b.F + L.seq_off;
+    f.n = L.n; f.Ls = L.Ls;
+    const DevParams *__restrict__ P = b.P;
+    const int n = L.n;
+    const int md = (start == 1) ? L.Ls : L.Ls + 1;   // final backtrack(1, L*) vs backtrack(i+1, L*+1)
+
+    char *st = b.slots + g * (unsigned long long)b.slot_stride;
+    const int ndash = min(n - start, md) + 1;
+    for (int k = lane; k < b.slot_stride; k += 32) st[k] = k < ndash ? '-' : 0;
+    __syncwarp();
+
+    int *stk = b.stack_scratch + g * (unsigned long long)b.stack_cap * 2ULL;
+    int sp = 0;
+    bool failed = false;
+#define PUSH(a_, b_, ml_)                                                      \
+    do {                                                                       \
+        if (sp < b.stack_cap) {                                                \
+            if (lane == 0) { stk[2 * sp] = (a_); stk[2 * sp + 1] = ((b_) << 1) | (ml_); } \
+            sp++;                                                              \
+        } else failed = true;                                                  \
+    } while (0)
+    PUSH(start, min(n, start + md + 1), 0);
+    __syncwarp();
+
+    while (sp > 0 && !failed) {
+        sp--;
+        __syncwarp();
+        int i = stk[2 * sp];
+        int j = stk[2 * sp + 1];
+        const int ml = j & 1;
+        j >>= 1;
+        if (j < i + 4) continue;
+        if (ml == 0) {
+            const int fij = f.f(i);
+            if (fij == f.f(i + 1)) { PUSH(i + 1, j, 0); continue; }
+            int traced = 0, jj = 0, kk = 0;
+            for (int kb = i + 4; kb <= j; kb += 32) {
+                const int k = kb + lane;
+                int tr = 0, myjj = k + 1;
+                if (k <= j) {
+                    int t = f.type(i + 1, k);
+                    if (t) {
+                        const int cc = f.c(i + 1, k) + P->dangle5[t * 5 + f.S1(i)] + f.AU(t);
+                        if (fij == cc + f.f(k + 1)) tr = i + 1;
+                        if (k < n && fij == f.f(k + 2) + cc + P->dangle3[t * 5 + f.S1(k + 1)]) { tr = i + 1; myjj = k + 2; }
+                    }
+                    t = f.type(i, k);
+                    if (t) {
+                        const int cc = f.c(i, k) + f.AU(t);
+                        if (fij == cc + f.f(k + 1)) tr = i;
+                        if (k < n && fij == f.f(k + 2) + cc + P->dangle3[t * 5 + f.S1(k + 1)]) { tr = i; myjj = k + 2; }
+                    }
+                }
+                const unsigned hit = __ballot_sync(FULL, tr != 0);
+                if (hit) {
+                    const int src = __ffs(hit) - 1;
+                    traced = __shfl_sync(FULL, tr, src);
+                    jj = __shfl_sync(FULL, myjj, src);
+                    kk = kb + src;
+                    break;
+                }
+            }
+            if (!traced) { failed = true; break; }
+            if (j == n) PUSH(jj, j, 0);
+            i = traced; j = kk;
+            if (lane == 0) {
+                st[i - start] = '('; st[j - start] = ')';
+                if (jj == j + 2 && j < n) st[j + 1 - start] = '.';
+            }
+        } else {
+            const int fij = f.m(i, j);
+            if (f.m(i, j - 1) == fij) { PUSH(i, j - 1, 1); continue; }
+            if (f.m(i + 1, j) == fij) { PUSH(i + 1, j, 1); continue; }
+            int t = f.type(i, j);
+            const int cij = f.c(i, j) + P->MLintern[t];
+            t = f.type(i + 1, j);
+            const int ci1j = f.c(i + 1, j) + P->dangle5[t * 5 + f.S1(i)] + P->MLintern[t];
+            t = f.type(i, j - 1);
+            const int cij1 = f.c(i, j - 1) + P->dangle3[t * 5 + f.S1(j)] + P->MLintern[t];
+            t = f.type(i + 1, j - 1);
+            const int ci1j1 = f.c(i + 1, j - 1) + P->dangle5[t * 5 + f.S1(i)] + P->dangle3[t * 5 + f.S1(j)] + P->MLintern[t];
+            if (fij == cij || fij == ci1j || fij == cij1 || fij == ci1j1) {
+                if (fij == ci1j) i++;
+                else if (fij == cij1) j--;
+                else if (fij == ci1j1) { i++; j--; }
+                if (lane == 0) { st[i - start] = '('; st[j - start] = ')'; }
+            } else {
+                int ksplit = -1;
+                for (int kb = i + 4; kb <= j - 5; kb += 32) {
+                    const int k = kb + lane;
+                    const bool ok = (k <= j - 5) && (fij == f.m(i, k) + f.m(k + 1, j));
+                    const unsigned hit = __ballot_sync(FULL, ok);
+                    if (hit) { ksplit = kb + __ffs(hit) - 1; break; }
+                }
+                if (ksplit < 0) { failed = true; break; }
+                PUSH(i, ksplit, 1);
+                PUSH(ksplit + 1, j, 1);
+                continue;
+            }
+        }
+        // "repeat": (i,j) pairs; follow stacks / interior loops until a hairpin or multiloop
+        for (;;) {
+            const int cij = f.c(i, j), t = f.type(i, j);
+            if (cij == tb_hairpin(f, i, j, t)) break;
+            const int d = j - i;
+            const int K = min(30, d - 6);
+            int np = 0, nq = 0;
+            bool found = false;
+            if (K >= 0) {
+                for (int cb = 0; cb < 496; cb += 32) {
+                    const int m = cb + lane;
+                    bool ok = false;
+                    int p = 0, q = 0;
+                    if (m < 496) {
+                        const int u = P->uv[m][0], v = P->uv[m][1];
+                        if (u + v <= K) {
+                            p = i + 1 + u; q = j - 1 - v;
+                            const int t2 = f.type(p, q);
+                            if (t2) ok = (cij == tb_loop_energy(f, i, j, p, q, t, P->rtype[t2]) + f.c(p, q));
+                        }
+                    }
+                    const unsigned hit = __ballot_sync(FULL, ok);
+                    if (hit) {
+                        const int src = __ffs(hit) - 1;
+                        np = __shfl_sync(FULL, p, src);
+                        nq = __shfl_sync(FULL, q, src);
+                        found = true;
+                        break;
+                    }
+                    // rows u > K contribute nothing; entries are u-major, so stop once u exceeds K
+                    if (P->uv[min(cb + 31, 495)][0] > K && P->uv[cb][0] > K) break;
+                }
+            }
+            if (found) {
+                i = np; j = nq;
+                if (lane == 0) { st[i - start] = '('; st[j - start] = ')'; }
+                continue;
+            }
+            // multiloop decomposition
+            const int tt = P->rtype[t];
+            const int mm = P->MLclosing + P->MLintern[tt];
+            const int d5 = P->dangle5[tt * 5 + f.S1(j - 1)], d3 = P->dangle3[tt * 5 + f.S1(i + 1)];
+            int ksplit = -1, which = 0;
+            for (int kb = i + 5; kb <= j - 6; kb += 32) {
+                const int k = kb + lane;
+                int w = 0;
+                if (k <= j - 6) {
+                    const int a1 = f.m(i + 1, k), a2 = f.m(i + 2, k), b1 = f.m(k + 1, j - 1), b2 = f.m(k + 1, j - 2);
+                    if (cij == a1 + b1 + mm) w = 1;
+                    else if (cij == a2 + b1 + mm + d3) w = 2;
+                    else if (cij == a1 + b2 + mm + d5) w = 3;
+                    else if (cij == a2 + b2 + mm + d3 + d5) w = 4;
+                }
+                const unsigned hit = __ballot_sync(FULL, w != 0);
+                if (hit) {
+                    const int src = __ffs(hit) - 1;
+                    ksplit = kb + src;
+                    which = __shfl_sync(FULL, w, src);
+                    break;
+                }
+            }
+            if (ksplit < 0) { failed = true; break; }
+            const int i1 = (which == 2 || which == 4) ? i + 2 : i + 1;
+            const int j1 = (which == 3 || which == 4) ? j - 2 : j - 1;
+            PUSH(i1, ksplit, 1);
+            PUSH(ksplit + 1, j1, 1);
+            break;
+        }
+    }
+#undef PUSH
+    __syncwarp();
+    if (failed) {
+        if (lane == 0) { atomicExch(b.fail_flag, 1); b.tb_len[g] = 0; b.tb_start[g] = start; b.tb_locus[g] = l; }
+        return;
+    }
+    // finalise (Lfold.c:765-768): C string ends at first NUL; strip trailing '-'; '-' -> '.'
+    int len0 = b.slot_stride;
+    for (int kb = 0; kb < b.slot_stride; kb += 32) {
+        const int k = kb + lane;
+        const unsigned z = __ballot_sync(FULL, k < b.slot_stride && st[k] == 0);
+        if (z) { len0 = kb + __ffs(z) - 1; break; }
+    }
+    int last = 0;  // last index with a non-dash char (index 0 is never stripped)
+    for (int kb = 0; kb < len0; kb += 32) {
+        const int k = kb + lane;
+        const unsigned nz = __ballot_sync(FULL, k < len0 && st[k] != '-');
+        if (nz) last = max(last, kb + 31 - __clz(nz));
+    }
+    const int len = last + 1;
+    for (int k = lane; k < b.slot_stride; k += 32) {
+        if (k < len) { if (st[k] == '-') st[k] = '.'; }
+        else st[k] = 0;
+    }
+    if (lane == 0) { b.tb_len[g] = len; b.tb_start[g] = start; b.tb_locus[g] = l; }
+}
+
+cudaError_t launch_traceback(const TraceBuffers &b, cudaStream_t st)
+{
+    if (b.ntb == 0) return cudaSuccess;
+    const unsigned long long blocks = (b.ntb + 3) / 4;
+    k_traceback<<<(unsigned)blocks, 128, 0, st>>>(b);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------ emit
+// one warp per traceback: decide whether RNALfold prints it (A.5)
+__global__ void __launch_bounds__(128) k_emit(TraceBuffers b)
+{
+    const unsigned long long g = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (g >= b.ntb) return;
+    const int l = b.tb_locus[g];
+    const LocusDesc L = b.loci[l];
+    const int kidx = (int)(g - b.tb_base[l]), cnt = b.tb_count[l];
+    const int start = b.tb_start[g], len = b.tb_len[g];
+    const int *F = b.F + L.seq_off;
+    bool printed;
+    const bool last_is_final = (b.tb_start[b.tb_base[l] + cnt - 1] == 1);
+    const int last_regular = last_is_final ? cnt - 2 : cnt - 1;
+    if (kidx >= last_regular) printed = true;   // last "prev" at i==1, and the final backtrack(1,L*)
+    else {
+        // next traceback (ss) against this one (prev): prev_i = start, i = start_next - 1
+        const unsigned long long gn = g + 1;
+        const int i = b.tb_start[gn] - 1, ls = b.tb_len[gn];
+        const char *ss = b.slots + gn * (unsigned long long)b.slot_stride;
+        const char *prev = b.slots + g * (unsigned long long)b.slot_stride;
+        if (i + ls < start + len) printed = true;
+        else {
+            const int off = start - i;
+            bool diff = false;
+            for (int kb = 0; kb < len && !diff; kb += 32) {
+                const int k = kb + lane;
+                const bool dneq = (k < len) && (ss[off + k] != prev[k]);
+                diff = __any_sync(FULL, dneq);
+            }
+            printed = diff;
+        }
+    }
+    if (lane == 0) {
+        b.tb_flag[g] = printed ? 1 : 0;
+        const int a = F[start];
+        const int e2 = (start + len <= L.n + 2) ? F[start + len] : 0;
+        b.tb_energy[g] = a - e2;
+    }
+}
+
+cudaError_t launch_emit(const TraceBuffers &b, cudaStream_t st)
+{
+    if (b.ntb == 0) return cudaSuccess;
+    const unsigned long long blocks = (b.ntb + 3) / 4;
+    k_emit<<<(unsigned)blocks, 128, 0, st>>>(b);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------ pack
+__global__ void __launch_bounds__(128) k_pack(TraceBuffers b, const unsigned long long *__restrict__ ss_off,
+                                              const unsigned long long *__restrict__ hit_idx, char *__restrict__ arena,
+                                              int *__restrict__ out_start, int *__restrict__ out_len,
+                                              int *__restrict__ out_energy, unsigned long long *__restrict__ out_ssoff)
+{
+    const unsigned long long g = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (g >= b.ntb || !b.tb_flag[g]) return;
+    const int len = b.tb_len[g];
+    const char *src = b.slots + g * (unsigned long long)b.slot_stride;
+    char *dst = arena + ss_off[g];
+    for (int k = lane; k <= len; k += 32) dst[k] = k < len ? src[k] : 0;
+    if (lane == 0) {
+        const unsigned long long h = hit_idx[g];
+        out_start[h] = b.tb_start[g];
+        out_len[h] = len;
+        out_energy[h] = b.tb_energy[g];
+        out_ssoff[h] = ss_off[g];
+    }
+}
+
+cudaError_t launch_pack(const TraceBuffers &b, const unsigned long long *ss_off, const unsigned long long *hit_idx,
+                        char *arena, int *out_start, int *out_len, int *out_energy, unsigned long long *out_ssoff,
+                        cudaStream_t st)
+{
+    if (b.ntb == 0) return cudaSuccess;
+    const unsigned long long blocks = (b.ntb + 3) / 4;
+    k_pack<<<(unsigned)blocks, 128, 0, st>>>(b, ss_off, hit_idx, arena, out_start, out_len, out_energy, out_ssoff);
+    return cudaGetLastError();
+}

@@ -1,0 +1,218 @@
+"""Host layer of the fold stage: the Python side of the drop-in boundary.
+
+Mirrors the reference's fold-stage interface (/root/reference/miR_PREFeR.py):
+  * fold_use_RNALfold(fastas, tmpdir, options, maxspan, chunksize)      MP:3047-3119
+      -> MirFold.fold_fasta_files(): same inputs (FASTA shard paths, span), same outputs
+         (one `<prefix>_rnalfoldoutput_<i>` text file per shard, byte-identical to RNALfold's).
+  * `RNALfold -L <n>` stdin/stdout contract                              MP:3053, :3064
+      -> MirFold.fold_text(): RNALfold-identical text for arbitrary RNALfold input text.
+  * the hairpin lines parsed by get_structures_next_extendregion()       MP:1566-1573
+      -> FoldResult.hits(r): (ss, energy_dcal, start) tuples without any text round trip.
+
+All arithmetic happens in libmirfold.so on the GPU; this file only moves bytes.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _lib
+from ._lib import MirfoldError
+
+DEFAULT_PARAMSET = b"vienna-1.8.5-d1"
+HIT_DTYPE = np.dtype([("start", "<i4"), ("len", "<i4"), ("mfe_dcal", "<i4"), ("reserved", "<i4"), ("ss_off", "<u8")])
+
+
+class FoldResult:
+    """Owns a mirfold_result.  Hit order inside a record is RNALfold's print order."""
+
+    def __init__(self, lib, ptr, nseq):
+        self._lib = lib
+        self._ptr = ptr
+        r = ptr.contents
+        self.nseq = int(r.nseq)
+        self.nhits = int(r.nhits)
+        self.ss_bytes = int(r.ss_bytes)
+        self.stats = r.stats.as_dict()
+        self.downloaded = bool(r.ss_arena) or self.nhits == 0
+        self.hit_begin = self.total_mfe_dcal = self.hit_table = self.arena = None
+        if self.downloaded:
+            if self.nseq:
+                self.hit_begin = np.ctypeslib.as_array(r.hit_begin, shape=(self.nseq + 1,))
+                self.total_mfe_dcal = np.ctypeslib.as_array(r.total_mfe_dcal, shape=(self.nseq,))
+            else:
+                self.hit_begin, self.total_mfe_dcal = np.zeros(1, np.uint64), np.zeros(0, np.int32)
+            if self.nhits:
+                raw = np.ctypeslib.as_array(C.cast(r.hits, C.POINTER(C.c_uint8)), shape=(self.nhits * C.sizeof(_lib.Hit),))
+                self.hit_table = raw.view(HIT_DTYPE)
+                self.arena = np.ctypeslib.as_array(C.cast(r.ss_arena, C.POINTER(C.c_uint8)), shape=(self.ss_bytes,))
+            else:
+                self.hit_table, self.arena = np.zeros(0, HIT_DTYPE), np.zeros(0, np.uint8)
+
+    def hits(self, r):
+        """[(dot_bracket, energy_dcal, start_1based)] of record r."""
+        b, e = int(self.hit_begin[r]), int(self.hit_begin[r + 1])
+        out = []
+        for h in self.hit_table[b:e]:
+            o, n = int(h["ss_off"]), int(h["len"])
+            out.append((self.arena[o:o + n].tobytes().decode("ascii"), int(h["mfe_dcal"]), int(h["start"])))
+        return out
+
+    def total(self, r):
+        return int(self.total_mfe_dcal[r])
+
+    def close(self):
+        if self._ptr is not None:
+            self.hit_begin = self.total_mfe_dcal = self.hit_table = self.arena = None
+            self._lib.mirfold_free_result(self._ptr)
+            self._ptr = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def convert_sequence(tok):
+    """RNALfold main(): upper-case, T->U."""
+    return tok.upper().replace("T", "U")
+
+
+def parse_rnalfold_input(text):
+    """Split RNALfold stdin into ('echo', line) / ('seq', token) items exactly like RNALfold's main():
+    lines starting with '>' or '*' and empty lines are echoed; '@' ends; the first whitespace-delimited
+    token of any other line is a sequence."""
+    items = []
+    lines = text.split("\n")
+    if lines and lines[-1] == "":
+        lines.pop()
+    for line in lines:
+        if line == "" or line[0] in ">*":
+            items.append(("echo", line))
+            continue
+        if line == "@":
+            break
+        tok = line.split(None, 1)
+        items.append(("seq", tok[0] if tok else ""))
+    return items
+
+
+def format_record(seq_token, hits, total_dcal):
+    out = []
+    for ss, e, start in hits:
+        out.append("%s (%6.2f) %4d\n" % (ss, e / 100., start))
+    out.append("%s\n (%6.2f)\n" % (convert_sequence(seq_token), total_dcal / 100.))
+    return "".join(out)
+
+
+class MirFold:
+    """A libmirfold context (one per process; `devices` = CUDA ordinals, default current device)."""
+
+    def __init__(self, devices=None, param_set=DEFAULT_PARAMSET):
+        self._lib = _lib.load()
+        self._ctx = C.c_void_p()
+        if devices:
+            arr = (C.c_int * len(devices))(*devices)
+            rc = self._lib.mirfold_open(C.byref(self._ctx), arr, len(devices), param_set)
+        else:
+            rc = self._lib.mirfold_open(C.byref(self._ctx), None, 0, param_set)
+        if rc != 0:
+            raise MirfoldError(rc, self._lib.mirfold_strerror(rc).decode())
+
+    def close(self):
+        if self._ctx:
+            self._lib.mirfold_close(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _raise(self, rc):
+        raise MirfoldError(rc, "%s (%s)" % (self._lib.mirfold_strerror(rc).decode(),
+                                            self._lib.mirfold_last_error(self._ctx).decode()))
+
+    @staticmethod
+    def pack(seqs):
+        """list of str/bytes -> (uint8 buffer, uint64 offsets)."""
+        bs = [s.encode("ascii") if isinstance(s, str) else bytes(s) for s in seqs]
+        off = np.zeros(len(bs) + 1, np.uint64)
+        if bs:
+            off[1:] = np.cumsum([len(b) for b in bs], dtype=np.uint64)
+        buf = np.frombuffer(b"".join(bs), np.uint8) if bs else np.zeros(0, np.uint8)
+        return buf, off
+
+    def fold_packed(self, buf, off, span):
+        """buf: uint8 array of concatenated raw sequence tokens, off: uint64[nseq+1]."""
+        buf = np.ascontiguousarray(buf, np.uint8)
+        off = np.ascontiguousarray(off, np.uint64)
+        nseq = len(off) - 1
+        res = C.POINTER(_lib.Result)()
+        rc = self._lib.mirfold_fold(self._ctx, buf.ctypes.data_as(C.c_void_p), off.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                    nseq, int(span), 0, C.byref(res))
+        if rc != 0:
+            self._raise(rc)
+        return FoldResult(self._lib, res, nseq)
+
+    def fold(self, seqs, span):
+        buf, off = self.pack(seqs)
+        return self.fold_packed(buf, off, span)
+
+    def fold_device(self, d_ptr, off, span, stream=None):
+        """Kernel-only path: raw sequences already in HBM at d_ptr (int), results stay on device."""
+        off = np.ascontiguousarray(off, np.uint64)
+        res = C.POINTER(_lib.Result)()
+        rc = self._lib.mirfold_fold_device(self._ctx, C.c_void_p(d_ptr), None, off.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                           len(off) - 1, int(span), 0, C.c_void_p(stream or 0), C.byref(res))
+        if rc != 0:
+            self._raise(rc)
+        return FoldResult(self._lib, res, len(off) - 1)
+
+    def debug_matrices(self, seq, span):
+        """(c, fML, f3) of one sequence in the oracle's [i][d] layout (tests only)."""
+        b = seq.encode() if isinstance(seq, str) else seq
+        n = len(b)
+        W = min(span, n) + 6
+        c = np.empty((n + 2, W), np.int32)
+        m = np.empty((n + 2, W), np.int32)
+        f3 = np.empty(n + 4, np.int32)
+        rc = self._lib.mirfold_debug_matrices(self._ctx, b, n, int(span), c.ctypes.data_as(C.c_void_p),
+                                              m.ctypes.data_as(C.c_void_p), f3.ctypes.data_as(C.c_void_p))
+        if rc != 0:
+            self._raise(rc)
+        return c, m, f3
+
+    # ---- RNALfold CLI contract -------------------------------------------------------------
+    def fold_text(self, text, span):
+        """RNALfold-identical stdout for RNALfold-style stdin text (`RNALfold -L span`)."""
+        items = parse_rnalfold_input(text)
+        seqs = [tok for kind, tok in items if kind == "seq"]
+        out = []
+        with self.fold(seqs, span) as res:
+            r = 0
+            for kind, tok in items:
+                if kind == "echo":
+                    out.append(tok + "\n")
+                else:
+                    out.append(format_record(tok, res.hits(r), res.total(r)))
+                    r += 1
+        return "".join(out)
+
+    def fold_fasta_files(self, fastas, outnames, span):
+        """fold_use_RNALfold() replacement: fold every FASTA shard, write RNALfold-format outputs."""
+        for fa, outname in zip(fastas, outnames):
+            with open(fa) as f:
+                text = f.read()
+            with open(outname + ".tmp", "w") as f:
+                f.write(self.fold_text(text, span))
+            os.rename(outname + ".tmp", outname)   # atomic, like MP:3098
+        return list(outnames)
