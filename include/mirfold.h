@@ -111,6 +111,11 @@ int mirfold_debug_matrices(mirfold_ctx *ctx, const char *seq, uint32_t n, int sp
 
 void mirfold_free_result(mirfold_result *res);
 
+/* Measurement aid (bench.py roofline denominator): sustained rate of independent min-plus terms
+ * (one add + one min each) on device 0 of the context, terms per second, for plain add+min code and
+ * for the DPX intrinsic __viaddmin_s32. */
+int mirfold_int_peak(mirfold_ctx *ctx, double *addmin_terms_per_s, double *dpx_terms_per_s);
+
 const char *mirfold_strerror(int code);
 /* Human-readable detail of the last error raised in this context (CUDA error string etc). */
 const char *mirfold_last_error(const mirfold_ctx *ctx);

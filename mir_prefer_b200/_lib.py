@@ -53,7 +53,7 @@ class DuplexVerdict(C.Structure):
 # every symbol include/mirfold.h declares
 EXPORTS = ["mirfold_open", "mirfold_close", "mirfold_fold", "mirfold_fold_device", "mirfold_debug_matrices",
            "mirfold_free_result", "mirfold_strerror", "mirfold_last_error", "mirfold_version", "mirfold_duplex",
-           "mirfold_duplex_fail_name"]
+           "mirfold_duplex_fail_name", "mirfold_int_peak"]
 
 _lib = None
 
@@ -92,5 +92,7 @@ def load():
     lib.mirfold_duplex.restype = C.c_int
     lib.mirfold_duplex_fail_name.argtypes = [C.c_int]
     lib.mirfold_duplex_fail_name.restype = C.c_char_p
+    lib.mirfold_int_peak.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.mirfold_int_peak.restype = C.c_int
     _lib = lib
     return lib

@@ -6,12 +6,18 @@
 // reference's row-by-row loop (results are bit-identical, the order of evaluation is not):
 //   * DML(i,j) = min_k fML(i,k)+fML(k+1,j) only reads diagonals <= d-5, so it is produced in
 //     strips of five diagonals ahead of the wavefront (phase A), one thread per row with the
-//     five running minima in registers: one fML(i,k) load feeds five min-plus terms.
+//     five running minima in registers: one fML(i,k) load feeds five min-plus terms.  The band is
+//     rectangular diagonal-major with a compile-time stride, so all operand addresses of the
+//     unrolled loop are one pointer + immediates.
 //   * the <=30-nt interior-loop search is a min-plus stencil over the previous 31 diagonals:
 //     generic loops use Cm(p,q) = c(p,q)+mismatchI[rtype][..] (+INF if (p,q) cannot pair) and a
-//     per-(u,v) constant, so no pair-type test is needed; a warp evaluates the 496 (u,v) terms
-//     of one typed cell in 16 fully-populated iterations (diagonals s and 30-s share a warp)
-//     and finishes with a warp min-reduction (redux.sync).
+//     per-(u,v) constant, so no pair-type test is needed.  The 33-diagonal Cm window lives in a
+//     shared-memory ring; a warp evaluates the 496 (u,v) terms of one typed cell in 16
+//     fully-populated iterations (loop sizes s and 30-s share a warp; per-lane ring offsets and
+//     constants are set up once per diagonal, the inner loop is LDS + VIADDMNMX) and finishes
+//     with redux.sync.  Bulges reuse the ring through a byte ring of (AU - mismatch) deltas.
+//   * the 7 table-driven two-loops (stack, 1-nt bulges, 1x1, 1x2, 2x1, 2x2), the hairpin and the
+//     d1 multiloop closing are evaluated lane-per-cell for 32 typed cells at a time.
 #include "mirfold_internal.cuh"
 
 // ------------------------------------------------------------------------------------ K1
@@ -97,14 +103,289 @@ __device__ __forceinline__ int dev_hairpin(const DevParams *__restrict__ P, cons
     return e;
 }
 
-// ------------------------------------------------------------------------------------ K2 (v1)
-// Dynamic smem: sS[n+3] | sS1[n+3] | pairtab[64] | list[n] (int)
-template <int NT>
-__global__ void __launch_bounds__(NT) k_fill(FillLaunch a)
+// the seven table-driven two-loops of a typed cell + hairpin + d1 multiloop closing (A.2, A.3)
+// Cb = band base of c; rD = DML ring [MF_RING_DML][NS]
+template <class StrideT>
+__device__ __forceinline__ int dev_cell_tail(const DevParams *__restrict__ P, const unsigned char *sS,
+                                             const unsigned char *sS1, const unsigned char *sPair,
+                                             const int *Cb, const int *rD, StrideT NS, int i,
+                                             int d, int t, int si1, int sj1, int K)
 {
-    extern __shared__ unsigned char smem_raw[];
+    const int j = i + d;
+    int best = MF_INF;
+#pragma unroll
+    for (int m = 0; m < 7; m++) {
+        const int u = (m == 1 || m == 3 || m == 4) ? 1 : (m >= 5 ? 2 : 0);
+        const int v = (m == 2 || m == 3 || m == 5) ? 1 : ((m == 4 || m == 6) ? 2 : 0);
+        // m: 0 (0,0)  1 (1,0)  2 (0,1)  3 (1,1)  4 (1,2)  5 (2,1)  6 (2,2)
+        if (u + v <= K) {
+            const int p = i + 1 + u, q = j - 1 - v;
+            const int t2 = sPair[sS[p] * 8 + sS[q]];
+            if (t2) {
+                const int e = dev_loop_energy(P, t, P->rtype[t2], u, v, si1, sj1, sS1[p - 1], sS1[q + 1]);
+                best = min(best, e + Cb[(q - p - 4) * NS + (p - 1)]);
+            }
+        }
+    }
+    best = min(best, dev_hairpin(P, sS, sS1, i, j, t));
+    const int tt = P->rtype[t];
+    const int d3 = P->dangle3[tt * 5 + si1], d5 = P->dangle5[tt * 5 + sj1];
+    int dec = MF_INF;
+    if (d - 2 >= 4) dec = rD[((d - 2) & (MF_RING_DML - 1)) * NS + i];                          // DML(i+1,j-1)
+    if (d - 3 >= 4) {
+        dec = min(dec, rD[((d - 3) & (MF_RING_DML - 1)) * NS + i + 1] + d3);                   // DML(i+2,j-1)
+        dec = min(dec, rD[((d - 3) & (MF_RING_DML - 1)) * NS + i] + d5);                       // DML(i+1,j-2)
+    }
+    if (d - 4 >= 4) dec = min(dec, rD[((d - 4) & (MF_RING_DML - 1)) * NS + i + 1] + d3 + d5);  // DML(i+2,j-2)
+    return min(best, P->MLclosing + P->MLintern[t] + dec);
+}
+
+// fML(i,j) from its six boundary terms + DML (A.3)
+template <class StrideT>
+__device__ __forceinline__ int dev_fml(const DevParams *__restrict__ P, const unsigned char *sS, const unsigned char *sS1,
+                                       const unsigned char *sPair, const int *Cb, const int *Mb,
+                                       const int *rD, StrideT NS, int i, int d, int Ls)
+{
+    const int j = i + d;
+    const int t = (d < Ls) ? sPair[sS[i] * 8 + sS[j]] : 0;
+    int m = MF_INF;
+    if (d - 1 >= 4) {
+        const int *Mp = Mb + (d - 5) * NS, *Cp = Cb + (d - 5) * NS;
+        m = min(Mp[i], Mp[i - 1]);                                  // fML(i+1,j), fML(i,j-1)
+        const int ta = sPair[sS[i + 1] * 8 + sS[j]];                // (i+1, j)
+        m = min(m, Cp[i] + P->dangle5[ta * 5 + sS1[i]] + P->MLintern[ta]);
+        const int tb = sPair[sS[i] * 8 + sS[j - 1]];                // (i, j-1)
+        m = min(m, Cp[i - 1] + P->dangle3[tb * 5 + sS1[j]] + P->MLintern[tb]);
+    }
+    m = min(m, Cb[(d - 4) * NS + i - 1] + P->MLintern[t]);
+    if (d - 2 >= 4) {
+        const int tc = sPair[sS[i + 1] * 8 + sS[j - 1]];            // (i+1, j-1)
+        m = min(m, Cb[(d - 6) * NS + i] + P->dangle5[tc * 5 + sS1[i]] + P->dangle3[tc * 5 + sS1[j]] + P->MLintern[tc]);
+    }
+    return min(m, rD[(d & (MF_RING_DML - 1)) * NS + i - 1]);
+}
+
+// phase A: DML for the strip d..d1 from fML diagonals <= d-1.  One (row, part) per thread; `part`
+// splits the e-range when the strip has fewer rows than the CTA has threads.
+template <int NT, class StrideT>
+__device__ __forceinline__ void dev_phase_a(const int *Mb, int *rD, StrideT NS, int n, int d,
+                                            int d1, int tid)
+{
+    const int emax = d1 - 5;  // e ranges 4..emax for the widest diagonal of the strip
+    if (emax < 4) return;
+    const int R = n - d;
+    const int Rpad = (R + 31) & ~31;
+    int nparts = NT / Rpad;
+    nparts = max(1, min(nparts, 8));
+    const int span = emax - 3;
+    const int per = (span + nparts - 1) / nparts;
+    for (int base = 0; base < Rpad * nparts; base += NT) {
+        const int idx = base + tid;
+        const int part = idx / Rpad, i = idx - part * Rpad + 1;
+        if (part >= nparts || i > R) continue;
+        const int e0 = 4 + part * per, e1 = min(emax, e0 + per - 1);
+        if (e0 > e1) continue;
+        const int ns = min(d1 - d, n - d - i) + 1;          // valid strip diagonals for this row
+        const int *pa = Mb + (e0 - 4) * NS + (i - 1);       // fML(i, i+e)
+        const int *pb = Mb + (d - 5 - e0) * NS + (i + e0);  // fML(i+e+1, i+d)   (+ s*NS for d+s)
+        int acc[5] = {MF_INF, MF_INF, MF_INF, MF_INF, MF_INF};
+        const int emain = min(e1, d - 5);                   // all five diagonals accept e <= d-5
+        int e = e0;
+        for (; e + 3 <= emain; e += 4) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int av = pa[k * NS];
+#pragma unroll
+                for (int s = 0; s < 5; s++)
+                    if (s < ns) acc[s] = min(acc[s], av + pb[s * NS - k * (NS - 1)]);
+            }
+            pa += 4 * NS;
+            pb -= 4 * (NS - 1);
+        }
+        for (; e <= emain; e++) {
+            const int av = pa[0];
+#pragma unroll
+            for (int s = 0; s < 5; s++)
+                if (s < ns) acc[s] = min(acc[s], av + pb[s * NS]);
+            pa += NS;
+            pb -= (NS - 1);
+        }
+        for (; e <= e1; e++) {   // tail: diagonal d+s accepts e <= d+s-5
+            const int av = pa[0];
+#pragma unroll
+            for (int s = 1; s < 5; s++)
+                if (s < ns && e <= d + s - 5) acc[s] = min(acc[s], av + pb[s * NS]);
+            pa += NS;
+            pb -= (NS - 1);
+        }
+#pragma unroll
+        for (int s = 0; s < 5; s++)
+            if (s < ns && acc[s] < MF_INF) {
+                int *dst = &rD[((d + s) & (MF_RING_DML - 1)) * NS + (i - 1)];
+                if (nparts == 1) *dst = acc[s];
+                else atomicMin(dst, acc[s]);
+            }
+    }
+}
+
+// ------------------------------------------------------------------------------------ K2 (shared-memory rings)
+#define MF_SLOTS 33   /* Cm ring: diagonals d-32 .. d */
+template <int NS>
+struct FillSmem {
+    static constexpr int cm_ints = (MF_SLOTS + 1) * NS;   // + one all-INF slot
+    static constexpr int dl_bytes = MF_SLOTS * NS;
+    static constexpr size_t bytes = (size_t)cm_ints * 4 + dl_bytes + 2 * (NS + 8) + 2 * NS + 16 * 32 * 4 + 64 + 16;
+};
+
+template <int NS, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) k_fill_smem(FillLaunch a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int *sCm = (int *)smem_raw;                                     // [34][NS]
+    unsigned char *sDl = (unsigned char *)(sCm + FillSmem<NS>::cm_ints);  // [33][NS]  AU - mismatchI + 70
+    unsigned char *sS = sDl + FillSmem<NS>::dl_bytes;               // [NS+8]
+    unsigned char *sS1 = sS + NS + 8;
+    unsigned short *sList = (unsigned short *)(sS1 + NS + 8);       // [NS]
+    int *sIlc = (int *)(sList + NS);                                // [16][32]
+    unsigned char *sPair = (unsigned char *)(sIlc + 16 * 32);       // [64]
+    __shared__ int sCount[2];
+
     const LocusDesc L = a.loci[blockIdx.x];
     const int n = L.n, Ls = L.Ls, dmax = L.dmax;
+    const DevParams *__restrict__ P = a.P;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    constexpr int NW = NT / 32;
+    constexpr int INFSLOT = MF_SLOTS * NS;
+
+    for (int k = tid; k < NS + 8; k += NT) {
+        const unsigned char b = (k < n + 3) ? a.codes[L.seq_off + k] : 0;
+        sS[k] = b & 7;
+        sS1[k] = b >> 4;
+    }
+    for (int k = tid; k < NS; k += NT) sCm[INFSLOT + k] = MF_INF;
+    for (int k = tid; k < 16 * 32; k += NT) sIlc[k] = P->ilc[k >> 5][k & 31];
+    if (tid < 64) sPair[tid] = P->pair[tid];
+    if (tid < 2) sCount[tid] = 0;
+
+    int *Cb = a.C + L.band_off;
+    int *Mb = a.M + L.band_off;
+    int *rD = a.ring + L.ring_off;   // [MF_RING_DML][NS]
+    for (int k = tid; k < MF_RING_DML * NS; k += NT) rD[k] = MF_INF;
+    __syncthreads();
+
+    // per-lane constants of the generic pass (INF = lane masked for this iteration)
+    int cst[16];
+    unsigned vmask = 0;
+#pragma unroll
+    for (int it = 0; it < 16; it++) {
+        const int c = sIlc[it * 32 + lane];
+        if (c < MF_INF) vmask |= 1u << it;
+        cst[it] = (c < MF_INF) ? c : 0;
+    }
+    const int nlB = lane + 2;                                          // bulge size handled by this lane
+    const int cstB = (nlB <= 30) ? P->bulge[nlB] - 70 : 0;
+
+    // typed list of the first diagonal
+    if (dmax >= 4) {
+        for (int i = tid + 1; i <= n - 4; i += NT) {
+            const int t = (4 < Ls) ? sPair[sS[i] * 8 + sS[i + 4]] : 0;
+            if (t) sList[atomicAdd(&sCount[0], 1)] = (unsigned short)i;
+            else { Cb[i - 1] = MF_INF; sCm[(4 % MF_SLOTS) * NS + i - 1] = MF_INF; }
+        }
+    }
+    __syncthreads();
+
+    for (int d = 4; d <= dmax; d++) {
+        if ((d - 4) % 5 == 0) {
+            dev_phase_a<NT>(Mb, rD, NS, n, d, min(d + 4, dmax), tid);
+            __syncthreads();
+        }
+        // ---------------- phase C: c on diagonal d (typed cells only)
+        const int ntyped = sCount[d & 1];
+        if (tid == 0) sCount[(d + 1) & 1] = 0;
+        const int K = min(30, d - 6);
+        const int bslot = (d - 2) % MF_SLOTS;
+        const int dslot = d % MF_SLOTS;
+        int off[16];
+#pragma unroll
+        for (int it = 0; it < 16; it++) {
+            int s, u;
+            if (it < 15) { if (lane <= it) { s = it; u = lane; } else { s = 30 - it; u = lane - it - 1; } }
+            else { s = 15; u = lane; }
+            int slot = bslot - s;
+            if (slot < 0) slot += MF_SLOTS;
+            off[it] = (s <= K && ((vmask >> it) & 1)) ? slot * NS + u : INFSLOT;
+        }
+        int offB1, offB2, offD1, offD2;
+        {
+            int slot = bslot - nlB;
+            if (slot < 0) slot += MF_SLOTS;
+            const bool ok = nlB <= K;                                   // K <= 30
+            offB1 = ok ? slot * NS + nlB : INFSLOT;                    // (u=nl, v=0): p = i+1+nl
+            offB2 = ok ? slot * NS : INFSLOT;                          // (u=0, v=nl): p = i+1
+            offD1 = ok ? slot * NS + nlB : 0;
+            offD2 = ok ? slot * NS : 0;
+        }
+        for (int c0 = wid * 32; c0 < ntyped; c0 += NW * 32) {
+            const int cnt = min(32, ntyped - c0);
+            int myG = MF_INF, myB = MF_INF;
+            for (int k = 0; k < cnt; k++) {
+                const int i = sList[c0 + k];
+                const int *w = sCm + i;
+                int g = MF_INF;
+#pragma unroll
+                for (int it = 0; it < 16; it++) g = min(g, w[off[it]] + cst[it]);
+                int bb = min(w[offB1] + (int)sDl[offD1 + i], w[offB2] + (int)sDl[offD2 + i]) + cstB;
+                g = warp_min(g);
+                bb = warp_min(bb);
+                if (lane == k) { myG = g; myB = bb; }
+            }
+            if (lane < cnt) {
+                const int i = sList[c0 + lane], j = i + d;
+                const int t = sPair[sS[i] * 8 + sS[j]];
+                const int si1 = sS1[i + 1], sj1 = sS1[j - 1];
+                int best = myG + P->mismatchI[(t * 5 + si1) * 5 + sj1];
+                best = min(best, myB + (t > 2 ? P->TerminalAU : 0));
+                best = min(best, dev_cell_tail(P, sS, sS1, sPair, Cb, rD, NS, i, d, t, si1, sj1, K));
+                const int tt = P->rtype[t];
+                const int mm = P->mismatchI[(tt * 5 + sS1[j + 1]) * 5 + sS1[i - 1]];
+                Cb[(d - 4) * NS + i - 1] = best;
+                sCm[dslot * NS + i - 1] = best + mm;
+                sDl[dslot * NS + i - 1] = (unsigned char)((tt > 2 ? P->TerminalAU : 0) - mm + 70);
+            }
+        }
+        __syncthreads();
+
+        // ---------------- phase M: fML on diagonal d; typed list + INF fill of diagonal d+1;
+        //                  reset of the DML ring slots of the next strip
+        const int ncell = n - d;
+        for (int i = tid + 1; i <= ncell; i += NT)
+            Mb[(d - 4) * NS + i - 1] = dev_fml(P, sS, sS1, sPair, Cb, Mb, rD, NS, i, d, Ls);
+        if (d + 1 <= dmax) {
+            const int dn = d + 1, nslot = dn % MF_SLOTS;
+            for (int i = tid + 1; i <= n - dn; i += NT) {
+                const int t = (dn < Ls) ? sPair[sS[i] * 8 + sS[i + dn]] : 0;
+                if (t) sList[atomicAdd(&sCount[dn & 1], 1)] = (unsigned short)i;
+                else { Cb[(dn - 4) * NS + i - 1] = MF_INF; sCm[nslot * NS + i - 1] = MF_INF; }
+            }
+            if ((dn - 4) % 5 == 0) {
+                for (int s = 0; s < 5; s++)
+                    for (int i = tid; i < n; i += NT) rD[((dn + s) & (MF_RING_DML - 1)) * NS + i] = MF_INF;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------ K2 (generic: any n)
+// Same algorithm with the Cm window in a global-memory ring (for loci longer than the largest
+// shared-memory bucket).  Dynamic smem: sS[npad] | sS1[npad] | pairtab[64] | list[n] (int)
+template <int NT>
+__global__ void __launch_bounds__(NT) k_fill_generic(FillLaunch a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const LocusDesc L = a.loci[blockIdx.x];
+    const int n = L.n, Ls = L.Ls, dmax = L.dmax, NS = L.stride;
     const DevParams *__restrict__ P = a.P;
     const int npad = (n + 3 + 15) & ~15;
     unsigned char *sS = smem_raw;
@@ -122,65 +403,22 @@ __global__ void __launch_bounds__(NT) k_fill(FillLaunch a)
         sS1[k] = b >> 4;
     }
     if (tid < 64) sPair[tid] = P->pair[tid];
+
+    int *Cb = a.C + L.band_off;
+    int *Mb = a.M + L.band_off;
+    int *rD = a.ring + L.ring_off;                              // [MF_RING_DML][NS]
+    int *rCm = rD + (unsigned long long)MF_RING_DML * NS;       // [MF_RING_CM][NS]
+    for (int k = tid; k < MF_RING_DML * NS; k += NT) rD[k] = MF_INF;
     __syncthreads();
 
-    int *__restrict__ C = a.C + L.band_off;
-    int *__restrict__ M = a.M + L.band_off;
-    int *__restrict__ rCm = a.ring + L.ring_off;                       // [MF_RING_CM][n]
-    int *__restrict__ rD = rCm + (unsigned long long)MF_RING_CM * n;   // [MF_RING_DML][n]
-
     for (int d = 4; d <= dmax; d++) {
-        // ---------------- phase A: DML for the strip d..d+4 (needs fML on diagonals <= d-1 only)
         if ((d - 4) % 5 == 0) {
-            const int d1 = min(d + 4, dmax);
-            const int R = n - d;                       // rows of the first strip diagonal
-            const int Rpad = (R + 31) & ~31;
-            int nparts = NT / Rpad;
-            nparts = max(1, min(nparts, 8));
-            // reset ring slots of the strip
-            for (int s = 0; s <= d1 - d; s++)
-                for (int i = tid; i < n; i += NT) rD[((d + s) & (MF_RING_DML - 1)) * n + i] = MF_INF;
-            __syncthreads();
-            const int emax = d1 - 5;                   // e ranges 4..emax (for the widest diagonal)
-            if (emax >= 4) {
-                const int span = emax - 4 + 1;
-                const int per = (span + nparts - 1) / nparts;
-                for (int base = 0; base < Rpad * nparts; base += NT) {
-                    const int idx = base + tid;
-                    const int part = idx / Rpad, i = idx - part * Rpad + 1;
-                    if (part < nparts && i <= R) {
-                        const int e0 = 4 + part * per, e1 = min(emax, e0 + per - 1);
-                        int acc[5] = {MF_INF, MF_INF, MF_INF, MF_INF, MF_INF};
-                        for (int e = e0; e <= e1; e++) {
-                            const int av = M[band_doff(n, e) + (i - 1)];   // fML(i, i+e)
-#pragma unroll
-                            for (int s = 0; s < 5; s++) {
-                                const int dd = d + s;              // target diagonal
-                                if (dd <= d1 && e <= dd - 5 && i <= n - dd) {
-                                    const int bv = M[band_doff(n, dd - 1 - e) + (i + e)];  // fML(i+e+1, i+dd)
-                                    acc[s] = min(acc[s], av + bv);
-                                }
-                            }
-                        }
-#pragma unroll
-                        for (int s = 0; s < 5; s++) {
-                            const int dd = d + s;
-                            if (dd <= d1 && i <= n - dd && acc[s] < MF_INF) {
-                                int *dst = &rD[(dd & (MF_RING_DML - 1)) * n + (i - 1)];
-                                if (nparts == 1) *dst = acc[s];
-                                else atomicMin(dst, acc[s]);
-                            }
-                        }
-                    }
-                }
-            }
+            dev_phase_a<NT>(Mb, rD, NS, n, d, min(d + 4, dmax), tid);
             __syncthreads();
         }
-
-        // ---------------- phase C: c on diagonal d
         const int ncell = n - d;
-        int *__restrict__ Cd = C + band_doff(n, d);
-        int *__restrict__ CmD = rCm + (d & (MF_RING_CM - 1)) * n;
+        int *Cd = Cb + (d - 4) * NS;
+        int *CmD = rCm + (d & (MF_RING_CM - 1)) * NS;
         if (tid == 0) sCount = 0;
         __syncthreads();
         for (int i = tid + 1; i <= ncell; i += NT) {
@@ -190,106 +428,98 @@ __global__ void __launch_bounds__(NT) k_fill(FillLaunch a)
         }
         __syncthreads();
         const int ntyped = sCount;
-        const int K = min(30, d - 6);   // largest u+v
+        const int K = min(30, d - 6);
         for (int c = wid; c < ntyped; c += NW) {
             const int i = sList[c], j = i + d;
             const int t = sPair[sS[i] * 8 + sS[j]];
             const int si1 = sS1[i + 1], sj1 = sS1[j - 1];
             int best = MF_INF;
-            // generic interior loops: 496 (u,v) terms, diagonals s and 30-s share an iteration
 #pragma unroll 4
             for (int it = 0; it < 16; it++) {
                 int s, u;
                 if (it < 15) { if (lane <= it) { s = it; u = lane; } else { s = 30 - it; u = lane - it - 1; } }
                 else { s = 15; u = lane; }
                 const int cst = P->ilc[it][lane];
-                if (s <= K && cst < MF_INF) {
-                    const int v = rCm[((d - 2 - s) & (MF_RING_CM - 1)) * n + (i + u)];  // Cm(i+1+u, .)
-                    best = min(best, v + cst);
-                }
+                if (s <= K && cst < MF_INF)
+                    best = min(best, rCm[((d - 2 - s) & (MF_RING_CM - 1)) * NS + (i + u)] + cst);
             }
             best += P->mismatchI[(t * 5 + si1) * 5 + sj1];
-            // special two-loops: stack, bulges, 1x1, 1x2, 2x1, 2x2 (65 terms)
-            for (int r = 0; r < 3; r++) {
-                const int m = lane + 32 * r;
-                int u, v;
-                if (m == 0) { u = 0; v = 0; }
-                else if (m <= 30) { u = m; v = 0; }
-                else if (m <= 60) { u = 0; v = m - 30; }
-                else if (m <= 64) { u = 1 + ((m - 61) >> 1); v = 1 + ((m - 61) & 1); }
-                else { u = 99; v = 99; }
-                if (u + v <= K) {
-                    const int p = i + 1 + u, q = j - 1 - v;
-                    const int t2 = sPair[sS[p] * 8 + sS[q]];
-                    if (t2) {
-                        const int e = dev_loop_energy(P, t, P->rtype[t2], u, v, si1, sj1, sS1[p - 1], sS1[q + 1]);
-                        best = min(best, e + C[band_doff(n, q - p) + (p - 1)]);
-                    }
+            // bulges of size >= 2 (58 terms): lanes 0..28 take (nl,0) and (0,nl)
+            {
+                const int nl = lane + 2;
+                if (nl <= K) {
+                    const int q1 = j - 1, p1 = i + 1 + nl, p2 = i + 1, q2 = j - 1 - nl;
+                    const int ta = sPair[sS[p1] * 8 + sS[q1]], tb = sPair[sS[p2] * 8 + sS[q2]];
+                    const int au = (t > 2 ? P->TerminalAU : 0), bl = P->bulge[nl];
+                    if (ta) best = min(best, Cb[(q1 - p1 - 4) * NS + p1 - 1] + bl + au + (ta > 2 ? P->TerminalAU : 0));
+                    if (tb) best = min(best, Cb[(q2 - p2 - 4) * NS + p2 - 1] + bl + au + (tb > 2 ? P->TerminalAU : 0));
                 }
             }
             best = warp_min(best);
             if (lane == 0) {
-                best = min(best, dev_hairpin(P, sS, sS1, i, j, t));
-                // multiloop closing with d1 dangles (A.3)
+                best = min(best, dev_cell_tail(P, sS, sS1, sPair, Cb, rD, NS, i, d, t, si1, sj1, K));
                 const int tt = P->rtype[t];
-                const int d3 = P->dangle3[tt * 5 + si1], d5 = P->dangle5[tt * 5 + sj1];
-                int dec = MF_INF;
-                if (d - 2 >= 4) dec = rD[((d - 2) & (MF_RING_DML - 1)) * n + i];                       // DML(i+1,j-1)
-                if (d - 3 >= 4) {
-                    dec = min(dec, rD[((d - 3) & (MF_RING_DML - 1)) * n + i + 1] + d3);                // DML(i+2,j-1)
-                    dec = min(dec, rD[((d - 3) & (MF_RING_DML - 1)) * n + i] + d5);                    // DML(i+1,j-2)
-                }
-                if (d - 4 >= 4) dec = min(dec, rD[((d - 4) & (MF_RING_DML - 1)) * n + i + 1] + d3 + d5);  // DML(i+2,j-2)
-                best = min(best, P->MLclosing + P->MLintern[t] + dec);
                 Cd[i - 1] = best;
                 CmD[i - 1] = best + P->mismatchI[(tt * 5 + sS1[j + 1]) * 5 + sS1[i - 1]];
             }
         }
         __syncthreads();
-
-        // ---------------- phase M: fML on diagonal d
-        int *__restrict__ Md = M + band_doff(n, d);
-        const int *__restrict__ Mp = (d - 1 >= 4) ? M + band_doff(n, d - 1) : nullptr;
-        const int *__restrict__ Cp = (d - 1 >= 4) ? C + band_doff(n, d - 1) : nullptr;
-        const int *__restrict__ Cpp = (d - 2 >= 4) ? C + band_doff(n, d - 2) : nullptr;
-        const int *__restrict__ Dd = rD + (d & (MF_RING_DML - 1)) * n;
-        for (int i = tid + 1; i <= ncell; i += NT) {
-            const int j = i + d;
-            const int t = (d < Ls) ? sPair[sS[i] * 8 + sS[j]] : 0;
-            int m = MF_INF;
-            if (Mp) m = min(Mp[i], Mp[i - 1]);                       // fML(i+1,j), fML(i,j-1)
-            m = min(m, Cd[i - 1] + P->MLintern[t]);
-            if (Cp) {
-                const int ta = sPair[sS[i + 1] * 8 + sS[j]];         // (i+1, j)
-                m = min(m, Cp[i] + P->dangle5[ta * 5 + sS1[i]] + P->MLintern[ta]);
-                const int tb = sPair[sS[i] * 8 + sS[j - 1]];         // (i, j-1)
-                m = min(m, Cp[i - 1] + P->dangle3[tb * 5 + sS1[j]] + P->MLintern[tb]);
-            }
-            if (Cpp) {
-                const int tc = sPair[sS[i + 1] * 8 + sS[j - 1]];     // (i+1, j-1)
-                m = min(m, Cpp[i] + P->dangle5[tc * 5 + sS1[i]] + P->dangle3[tc * 5 + sS1[j]] + P->MLintern[tc]);
-            }
-            m = min(m, Dd[i - 1]);
-            Md[i - 1] = m;
+        for (int i = tid + 1; i <= ncell; i += NT)
+            Mb[(d - 4) * NS + i - 1] = dev_fml(P, sS, sS1, sPair, Cb, Mb, rD, NS, i, d, Ls);
+        if (d + 1 <= dmax && (d + 1 - 4) % 5 == 0) {
+            for (int s = 0; s < 5; s++)
+                for (int i = tid; i < n; i += NT) rD[((d + 1 + s) & (MF_RING_DML - 1)) * NS + i] = MF_INF;
         }
         __syncthreads();
     }
 }
 
+template <int NS, int NT, int MINB>
+static cudaError_t launch_fill_bucket(const FillLaunch &a, int first, int count, cudaStream_t st)
+{
+    if (count <= 0) return cudaSuccess;
+    static bool configured = false;
+    const size_t smem = FillSmem<NS>::bytes;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_fill_smem<NS, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    FillLaunch b = a;
+    b.loci = a.loci + first;
+    b.nloci = count;
+    k_fill_smem<NS, NT, MINB><<<count, NT, smem, st>>>(b);
+    return cudaGetLastError();
+}
+
+// Loci arrive sorted by descending DP cells == descending n (for a fixed span), so each stride
+// bucket is a contiguous range [bucket_first[k], bucket_first[k+1]).
 cudaError_t launch_fill(const FillLaunch &a, cudaStream_t st)
 {
     if (a.nloci == 0) return cudaSuccess;
-    constexpr int NT = 512;
-    const int npad = (a.max_n + 3 + 15) & ~15;
-    const size_t smem = (size_t)2 * npad + 64 + (size_t)a.max_n * sizeof(int) + 16;
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_fill<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = smem;
+    cudaError_t e = cudaSuccess;
+    // generic (n > 608)
+    const int ng = a.bucket_first[1] - a.bucket_first[0];
+    if (ng > 0) {
+        constexpr int NT = 512;
+        const int npad = (a.max_n + 3 + 15) & ~15;
+        const size_t smem = (size_t)2 * npad + 64 + (size_t)a.max_n * sizeof(int) + 16;
+        static size_t configured = 0;
+        if (smem > 48 * 1024 && smem > configured) {
+            e = cudaFuncSetAttribute(k_fill_generic<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            configured = smem;
+        }
+        FillLaunch b = a;
+        b.loci = a.loci + a.bucket_first[0];
+        b.nloci = ng;
+        k_fill_generic<NT><<<ng, NT, smem, st>>>(b);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
-    k_fill<NT><<<a.nloci, NT, smem, st>>>(a);
-    return cudaGetLastError();
+    if ((e = launch_fill_bucket<608, 512, 2>(a, a.bucket_first[1], a.bucket_first[2] - a.bucket_first[1], st)) != cudaSuccess) return e;
+    if ((e = launch_fill_bucket<352, 384, 3>(a, a.bucket_first[2], a.bucket_first[3] - a.bucket_first[2], st)) != cudaSuccess) return e;
+    if ((e = launch_fill_bucket<160, 256, 4>(a, a.bucket_first[3], a.bucket_first[4] - a.bucket_first[3], st)) != cudaSuccess) return e;
+    return cudaSuccess;
 }
 
 // ------------------------------------------------------------------------------------ K3
@@ -301,7 +531,7 @@ __global__ void __launch_bounds__(128) k_f3(const LocusDesc *__restrict__ loci, 
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (w >= nloci) return;
     const LocusDesc L = loci[w];
-    const int n = L.n, Ls = L.Ls;
+    const int n = L.n, Ls = L.Ls, NS = L.stride;
     const unsigned char *__restrict__ cd = codes + L.seq_off;
     const int *__restrict__ C = Call + L.band_off;
     int *F = Fall + L.seq_off;
@@ -317,21 +547,21 @@ __global__ void __launch_bounds__(128) k_f3(const LocusDesc *__restrict__ loci, 
             const int f1 = F[j + 1], f2 = F[j + 2];
             int t = (d < Ls) ? P->pair[si * 8 + sj] : 0;
             if (t) {
-                const int e = C[band_doff(n, d) + (i - 1)] + (t > 2 ? AUp : 0);
+                const int e = C[(d - 4) * NS + (i - 1)] + (t > 2 ? AUp : 0);
                 best = min(best, min(e + f1, e + P->dangle3[t * 5 + s1j1] + f2));
             }
             t = (d - 1 >= 4) ? P->pair[si1 * 8 + sj] : 0;
             if (t) {
-                const int e = C[band_doff(n, d - 1) + i] + P->dangle5[t * 5 + s1i] + (t > 2 ? AUp : 0);
+                const int e = C[(d - 5) * NS + i] + P->dangle5[t * 5 + s1i] + (t > 2 ? AUp : 0);
                 best = min(best, min(e + f1, e + P->dangle3[t * 5 + s1j1] + f2));
             }
         }
         if (lane == 0 && n <= i + Ls) {
             const int d = n - i, sj = cd[n] & 7;
             int t = (d < Ls) ? P->pair[si * 8 + sj] : 0;
-            if (t) best = min(best, C[band_doff(n, d) + (i - 1)] + (t > 2 ? AUp : 0));
+            if (t) best = min(best, C[(d - 4) * NS + (i - 1)] + (t > 2 ? AUp : 0));
             t = (d - 1 >= 4) ? P->pair[si1 * 8 + sj] : 0;
-            if (t) best = min(best, C[band_doff(n, d - 1) + i] + P->dangle5[t * 5 + s1i] + (t > 2 ? AUp : 0));
+            if (t) best = min(best, C[(d - 5) * NS + i] + P->dangle5[t * 5 + s1i] + (t > 2 ? AUp : 0));
         }
         best = warp_min(best);
         if (lane == 0) F[i] = min(F[i + 1], best);

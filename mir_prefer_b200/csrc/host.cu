@@ -278,7 +278,8 @@ void run_device(Device &D, const char *seqs, const uint64_t *h_off, const std::v
     std::vector<Chunk> chunks;
     auto locus_bytes = [&](const Locus &l) {
         const int Ls = std::min(L, l.n), dmax = std::min(Ls, l.n - 1);
-        return (size_t)band_cells(l.n, dmax) * 8 + (size_t)l.n * (MF_RING_PER_NT * 4 + 5 + 2 * 4) + 4096;
+        const int stride = band_stride_for(l.n);
+        return (size_t)band_elems(stride, dmax) * 8 + (size_t)stride * MF_RING_PER_STRIDE * 4 + (size_t)l.n * 16 + 4096;
     };
     {
         size_t b = 0, acc = 0;
@@ -312,12 +313,13 @@ void run_device(Device &D, const char *seqs, const uint64_t *h_off, const std::v
             const Locus &l = loci[cb + k];
             LocusDesc &d = hl[k];
             d.n = l.n; d.Ls = std::min(L, l.n); d.dmax = std::min(d.Ls, l.n - 1); d.rec = (int)l.rec;
+            d.stride = band_stride_for(l.n);
             d.seq_off = seq_acc; d.band_off = band_acc; d.ring_off = ring_acc;
             d.raw_off = d_raw ? h_off[l.rec] : raw_acc;
             hlo[k] = list_acc;
             seq_acc += (unsigned long long)l.n + 3;
-            band_acc += band_cells(l.n, d.dmax);
-            ring_acc += (unsigned long long)l.n * MF_RING_PER_NT;
+            band_acc += band_elems(d.stride, d.dmax);
+            ring_acc += (unsigned long long)d.stride * MF_RING_PER_STRIDE;
             raw_acc += (unsigned long long)l.n;
             list_acc += (unsigned long long)l.n / 2 + 2;
             max_n = std::max(max_n, l.n); max_Ls = std::max(max_Ls, d.Ls);
@@ -355,7 +357,16 @@ void run_device(Device &D, const char *seqs, const uint64_t *h_off, const std::v
         const LocusDesc *dl = D.loci.as<LocusDesc>();
         CK(launch_prepare(raw_dev, dl, nl, seq_acc, D.codes.as<unsigned char>(), D.F.as<int>(), st));
         CK(cudaEventRecord(D.ev[2], st));
-        FillLaunch fa{dl, nl, max_n, D.codes.as<unsigned char>(), D.C.as<int>(), D.M.as<int>(), D.ring.as<int>(), D.dP};
+        FillLaunch fa{dl, nl, max_n, D.codes.as<unsigned char>(), D.C.as<int>(), D.M.as<int>(), D.ring.as<int>(), D.dP, {0, 0, 0, 0, 0}};
+        {   // loci are sorted by descending n: stride buckets are contiguous
+            int k = 0;
+            const int lim[3] = {608, 352, 160};
+            for (int b = 0; b < 3; b++) {
+                while (k < nl && hl[k].n > lim[b]) k++;
+                fa.bucket_first[b + 1] = k;
+            }
+            fa.bucket_first[4] = nl;
+        }
         CK(launch_fill(fa, st));
         CK(cudaEventRecord(D.ev[3], st));
         CK(launch_f3(dl, nl, D.codes.as<unsigned char>(), D.C.as<int>(), D.F.as<int>(), D.dP, st));
@@ -729,14 +740,18 @@ int mirfold_debug_matrices(mirfold_ctx *ctx, const char *seq, uint32_t n, int sp
     cudaStream_t st = D.stream;
     LocusDesc d{};
     d.n = (int)n; d.Ls = std::min(span_L, (int)n); d.dmax = std::min(d.Ls, (int)n - 1);
-    const unsigned long long cells = band_cells(d.n, d.dmax);
+    d.stride = band_stride_for(d.n);
+    const unsigned long long cells = band_elems(d.stride, d.dmax);
     CK(D.raw.ensure(n)); CK(D.loci.ensure(sizeof d)); CK(D.codes.ensure(n + 3)); CK(D.F.ensure((n + 3) * 4));
-    CK(D.C.ensure(cells * 4)); CK(D.M.ensure(cells * 4)); CK(D.ring.ensure((size_t)n * MF_RING_PER_NT * 4));
+    CK(D.C.ensure(cells * 4)); CK(D.M.ensure(cells * 4)); CK(D.ring.ensure((size_t)d.stride * MF_RING_PER_STRIDE * 4));
     CK(cudaMemcpyAsync(D.raw.p, seq, n, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(D.loci.p, &d, sizeof d, cudaMemcpyHostToDevice, st));
     const LocusDesc *dl = D.loci.as<LocusDesc>();
     CK(launch_prepare(D.raw.as<char>(), dl, 1, n + 3, D.codes.as<unsigned char>(), D.F.as<int>(), st));
-    FillLaunch fa{dl, 1, (int)n, D.codes.as<unsigned char>(), D.C.as<int>(), D.M.as<int>(), D.ring.as<int>(), D.dP};
+    FillLaunch fa{dl, 1, (int)n, D.codes.as<unsigned char>(), D.C.as<int>(), D.M.as<int>(), D.ring.as<int>(), D.dP, {0, 0, 0, 0, 1}};
+    fa.bucket_first[1] = d.n > 608 ? 1 : 0;
+    fa.bucket_first[2] = d.n > 352 ? 1 : 0;
+    fa.bucket_first[3] = d.n > 160 ? 1 : 0;
     CK(launch_fill(fa, st));
     CK(launch_f3(dl, 1, D.codes.as<unsigned char>(), D.C.as<int>(), D.F.as<int>(), D.dP, st));
     std::vector<int> hc(cells), hm(cells), hf(n + 3);
@@ -748,11 +763,23 @@ int mirfold_debug_matrices(mirfold_ctx *ctx, const char *seq, uint32_t n, int sp
     for (size_t k = 0; k < (size_t)(n + 2) * W; k++) c[k] = m[k] = MF_INF;
     for (int dd = 4; dd <= d.dmax; dd++)
         for (int i = 1; i <= (int)n - dd; i++) {
-            c[(size_t)i * W + dd] = hc[band_doff(d.n, dd) + (i - 1)];
-            m[(size_t)i * W + dd] = hm[band_doff(d.n, dd) + (i - 1)];
+            c[(size_t)i * W + dd] = hc[band_doff(d.stride, dd) + (i - 1)];
+            m[(size_t)i * W + dd] = hm[band_doff(d.stride, dd) + (i - 1)];
         }
     for (uint32_t k = 0; k < n + 3; k++) f3[k] = hf[k];
     f3[n + 3] = 0;
+    return MIRFOLD_OK;
+}
+
+int mirfold_int_peak(mirfold_ctx *ctx, double *addmin_terms_per_s, double *dpx_terms_per_s)
+{
+    if (!ctx || !addmin_terms_per_s || !dpx_terms_per_s) return MIRFOLD_ERR_ARG;
+    Device &D = ctx->devs[0];
+    cudaSetDevice(D.id);
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, D.id);
+    cudaError_t e = run_int_peak(D.stream, sms, addmin_terms_per_s, dpx_terms_per_s);
+    if (e != cudaSuccess) { ctx->last_error = cudaGetErrorString(e); return MIRFOLD_ERR_CUDA; }
     return MIRFOLD_OK;
 }
 

@@ -3,9 +3,11 @@
 // Data layout in HBM:
 //   codes : per locus n+3 bytes, index 0..n+2; byte = S | (S1 << 4); S[0]=S[n+1]=S[n+2]=0
 //   F     : per locus n+3 int32 at the same offsets (f3[0..n+2], f3[k>n-4]=0)
-//   C, M  : diagonal-major band per locus: diagonal d (=j-i, 4..dmax) holds cells i=1..n-d
-//           contiguously at band_off + band_doff(n,d) + (i-1).  dmax = min(L*, n-1).
-//           All threads walking one anti-diagonal therefore touch consecutive addresses.
+//   C, M  : diagonal-major band per locus, rectangular: diagonal d (=j-i, 4..dmax) holds cells
+//           i=1..n-d at band_off + (d-4)*stride + (i-1), stride = n rounded up to the locus'
+//           length bucket (a compile-time constant of the fill kernel, so that per-diagonal
+//           offsets become instruction immediates).  dmax = min(L*, n-1).  All threads walking
+//           one anti-diagonal touch consecutive addresses.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -37,24 +39,31 @@ struct LocusDesc {
     unsigned long long ring_off;  // into ring scratch (elements)
     unsigned long long raw_off;   // into the raw ASCII buffer
     int n;
-    int Ls;    // L* = min(L, n)
-    int dmax;  // min(Ls, n-1)
-    int rec;   // input record index
+    int Ls;      // L* = min(L, n)
+    int dmax;    // min(Ls, n-1)
+    int rec;     // input record index
+    int stride;  // band row stride (elements per diagonal)
+    int pad[3];
 };
 
-__host__ __device__ __forceinline__ unsigned long long band_doff(int n, int d)
+// offset of diagonal d inside a locus' band (elements)
+__host__ __device__ __forceinline__ unsigned int band_doff(int stride, int d) { return (unsigned int)(d - 4) * (unsigned int)stride; }
+__host__ __device__ __forceinline__ unsigned long long band_elems(int stride, int dmax)
 {
-    return (unsigned long long)(d - 4) * (unsigned long long)n -
-           ((unsigned long long)d * (unsigned long long)(d - 1) / 2ULL - 6ULL);
+    return dmax >= 4 ? (unsigned long long)(dmax - 3) * (unsigned long long)stride : 0ULL;
 }
-__host__ __device__ __forceinline__ unsigned long long band_cells(int n, int dmax)
+// length buckets of the shared-memory fill kernel; longer loci use the generic kernel
+__host__ __device__ __forceinline__ int band_stride_for(int n)
 {
-    return dmax >= 4 ? band_doff(n, dmax + 1) : 0ULL;
+    if (n <= 160) return 160;
+    if (n <= 352) return 352;
+    if (n <= 608) return 608;
+    return (n + 31) & ~31;
 }
 
-#define MF_RING_CM 64  /* Cm window ring (needs >= 33 diagonals) */
-#define MF_RING_DML 16 /* DML ring (needs >= 9 diagonals)        */
-#define MF_RING_PER_NT (MF_RING_CM + MF_RING_DML)
+#define MF_RING_CM 64  /* generic kernel: Cm window ring in global memory (needs >= 33 diagonals) */
+#define MF_RING_DML 16 /* DML ring (needs >= 9 diagonals)                                         */
+#define MF_RING_PER_STRIDE (MF_RING_CM + MF_RING_DML)
 
 // ---- kernel launchers (each defined next to its kernels) -------------------------------
 struct FillLaunch {
@@ -64,6 +73,7 @@ struct FillLaunch {
     const unsigned char *codes;
     int *C, *M, *ring;
     const DevParams *P;
+    int bucket_first[5];  // loci sorted by descending n: [generic | <=608 | <=352 | <=160 | end)
 };
 cudaError_t launch_prepare(const char *raw, const LocusDesc *loci, int nloci, unsigned long long total_codes,
                            unsigned char *codes, int *F, cudaStream_t st);
@@ -101,3 +111,4 @@ cudaError_t launch_emit(const TraceBuffers &b, cudaStream_t st);
 cudaError_t launch_pack(const TraceBuffers &b, const unsigned long long *ss_off, const unsigned long long *hit_idx,
                         char *arena, int *out_start, int *out_len, int *out_energy, unsigned long long *out_ssoff,
                         cudaStream_t st);
+cudaError_t run_int_peak(cudaStream_t st, int sm_count, double *addmin, double *dpx);

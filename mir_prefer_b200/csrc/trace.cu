@@ -50,7 +50,7 @@ struct Fold {
     const int *__restrict__ C;
     const int *__restrict__ M;
     const int *__restrict__ F;
-    int n, Ls;
+    int n, Ls, NS;
     __device__ __forceinline__ int S(int k) const { return cd[k] & 7; }
     __device__ __forceinline__ int S1(int k) const { return cd[k] >> 4; }
     __device__ __forceinline__ int type(int i, int j) const
@@ -63,7 +63,7 @@ struct Fold {
     {
         const int d = j - i;
         if (i < 1 || j > n || d < 4 || d > Ls) return MF_INF;
-        return A[band_doff(n, d) + (i - 1)];
+        return A[(d - 4) * NS + (i - 1)];
     }
     __device__ __forceinline__ int c(int i, int j) const { return band(C, i, j); }
     __device__ __forceinline__ int m(int i, int j) const { return band(M, i, j); }
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(128) k_traceback(TraceBuffers b)
     const int start = b.tb_start_list[b.list_off[l] + kidx];
     Fold f;
     f.P = b.P; f.cd = b.codes + L.seq_off; f.C = b.C + L.band_off; f.M = b.M + L.band_off; f.F = b.F + L.seq_off;
-    f.n = L.n; f.Ls = L.Ls;
+    f.n = L.n; f.Ls = L.Ls; f.NS = L.stride;
     const DevParams *__restrict__ P = b.P;
     const int n = L.n;
     const int md = (start == 1) ? L.Ls : L.Ls + 1;   // final backtrack(1, L*) vs backtrack(i+1, L*+1)

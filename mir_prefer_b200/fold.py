@@ -177,6 +177,14 @@ class MirFold:
             self._raise(rc)
         return FoldResult(self._lib, res, len(off) - 1)
 
+    def int_peak(self):
+        """Measured integer-issue roofline: (add+min terms/s, DPX terms/s) on this context's device."""
+        a, b = C.c_double(), C.c_double()
+        rc = self._lib.mirfold_int_peak(self._ctx, C.byref(a), C.byref(b))
+        if rc != 0:
+            self._raise(rc)
+        return a.value, b.value
+
     def debug_matrices(self, seq, span):
         """(c, fML, f3) of one sequence in the oracle's [i][d] layout (tests only)."""
         b = seq.encode() if isinstance(seq, str) else seq

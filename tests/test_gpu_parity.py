@@ -1,0 +1,195 @@
+"""GPU (-m gpu): libmirfold through the C ABI vs the oracle / golden RNALfold text, bit-exact."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, golden_cases
+from corpus import lcg_records, records_to_fasta, synth_loci
+
+pytestmark = pytest.mark.gpu
+
+
+def assert_same(mf, oracle, seqs, L):
+    with mf.fold(seqs, L) as res:
+        assert res.nseq == len(seqs)
+        for r, s in enumerate(seqs):
+            o = oracle.fold(s, L)
+            assert res.hits(r) == o["hits"], (r, len(s), L)
+            assert res.total(r) == o["total"], (r, len(s), L)
+        return res.stats
+
+
+@pytest.mark.parametrize("name,L", golden_cases())
+def test_fold_text_matches_reference_golden(mf, name, L):
+    """RNALfold CLI contract: byte-identical text to the reference binary's committed output."""
+    text = open(os.path.join(GOLDEN, name + ".in")).read()
+    want = open(os.path.join(GOLDEN, "%s.L%d.out" % (name, L))).read()
+    assert mf.fold_text(text, L) == want
+
+
+@pytest.mark.parametrize("seed", [3, 1, 2])
+def test_sha256_pins(mf, seed):
+    p = next(x for x in json.load(open(os.path.join(GOLDEN, "pins.json")))["pins"] if x["seed"] == seed)
+    text = records_to_fasta(lcg_records(p["seed"], p["nrec"], p["lo"], p["span"]))
+    out = mf.fold_text(text, p["L"])
+    assert len(out) == p["stdout_bytes"]
+    assert hashlib.sha256(out.encode()).hexdigest() == p["sha256_stdout"]
+
+
+def test_matrices_cell_for_cell(mf, oracle):
+    """c / fML / f3 against the oracle's intermediate matrices (which RNALfold cannot expose)."""
+    for s, L in ((synth_loci(5, 1, (60, 60))[0], 30), (synth_loci(6, 1, (320, 320))[0], 300),
+                 (synth_loci(7, 1, (400, 400))[0], 150), ("GC" * 40, 300)):
+        o = oracle.fold(s, L, matrices=True)
+        c, m, f3 = mf.debug_matrices(s, L)
+        n = len(s)
+        assert (o["c"] == c).all()
+        assert (np.minimum(o["m"], 1000000) == np.minimum(m, 1000000)).all()
+        assert (o["f3"][:n + 3] == f3[:n + 3]).all()
+
+
+def test_edge_lengths_and_empty(mf, oracle):
+    seqs = ["", "A", "ACG", "ACGU", "GCGCA", "GGGAAACCC", "GGGGAAAACCCC", "A" * 21, "ACGUNNNACGU", "N" * 50,
+            "GGGGGTTTTCCCCCAAAAGGGGGTTTTCCCCC"]
+    for L in (5, 6, 10, 30, 300):
+        assert_same(mf, oracle, seqs, L)
+    with mf.fold([], 300) as res:
+        assert res.nseq == 0 and res.nhits == 0
+
+
+def test_alphabet_iupac_lowercase(mf, oracle):
+    rng = np.random.default_rng(3)
+    seqs = ["".join(rng.choice(list("ACGUTacgutNnKXIRYkxi"), size=int(rng.integers(5, 200)))) for _ in range(60)]
+    assert_same(mf, oracle, seqs, 40)
+    assert_same(mf, oracle, seqs, 300)
+
+
+def test_sequence_families(mf, oracle):
+    rng = np.random.default_rng(4)
+    seqs = []
+    for k in range(30):
+        n = int(rng.integers(40, 420))
+        alpha, p = [("GC", None), ("AU", None), ("ACGU", [.15, .35, .35, .15]), ("ACGU", None)][k % 4]
+        seqs.append("".join(rng.choice(list(alpha), size=n, p=p)))
+    assert_same(mf, oracle, seqs, 300)
+    assert_same(mf, oracle, seqs, 61)
+
+
+def test_parity_config_sample(mf, oracle):
+    """cfg-2 shape (300-600 nt, L=300): seeded sample small enough for the oracle."""
+    assert_same(mf, oracle, synth_loci(1001, 48, "parity"), 300)
+
+
+def test_arabidopsis_length_law(mf, oracle):
+    assert_same(mf, oracle, synth_loci(1002, 48, "arabidopsis"), 300)
+
+
+def test_span_sweep(mf, oracle):
+    seqs = synth_loci(1004, 24, "sweep")
+    for L in (150, 300, 500):
+        assert_same(mf, oracle, seqs, L)
+
+
+def test_long_loci(mf, oracle):
+    assert_same(mf, oracle, synth_loci(1003, 2, "long") + synth_loci(12, 4, (1000, 2000)), 300)
+
+
+def test_against_reference_binary_live(mf, oracle):
+    """When the reference's own RNALfold travelled to this box (oracle/_ref), compare against it."""
+    if not oracle.have_rlf():
+        pytest.skip("oracle/_ref/RNALfold not staged")
+    text = records_to_fasta([("s%d" % k, s) for k, s in enumerate(synth_loci(88, 24, "parity"))])
+    assert mf.fold_text(text, 300) == oracle.fold_text(text, 300, binary=oracle.RLF)
+
+
+def test_chunking_is_invisible(oracle):
+    """Forcing many memory chunks must not change results (batch-composition independence)."""
+    import mir_prefer_b200 as mp
+    seqs = synth_loci(21, 40, (80, 400))
+    os.environ["MIRFOLD_MEM_BUDGET_MB"] = "2"
+    try:
+        with mp.MirFold() as small, small.fold(seqs, 300) as a:
+            assert a.stats["n_chunks"] > 3
+            got = [(a.hits(r), a.total(r)) for r in range(len(seqs))]
+    finally:
+        del os.environ["MIRFOLD_MEM_BUDGET_MB"]
+    assert got == [(o["hits"], o["total"]) for o in (oracle.fold(s, 300) for s in seqs)]
+
+
+def _check_structure_properties(res, lens, L):
+    hb = res.hit_begin
+    tab = res.hit_table
+    assert (tab["len"] >= 1).all() and (tab["len"] <= L + 2).all()
+    assert (tab["start"] >= 1).all()
+    arena = res.arena
+    # balanced brackets over the whole arena: every string is NUL-terminated, so a running depth
+    # that returns to 0 at each NUL proves each structure is balanced
+    depth = np.cumsum((arena == ord("(")).astype(np.int64) - (arena == ord(")")).astype(np.int64))
+    nul = np.flatnonzero(arena == 0)
+    assert (depth[nul] == 0).all()
+    assert set(np.unique(arena).tolist()) <= {0, ord("("), ord(")"), ord(".")}
+    rec_of_hit = np.repeat(np.arange(res.nseq), np.diff(hb).astype(np.int64))
+    assert (tab["start"] + tab["len"] - 1 <= lens[rec_of_hit]).all()
+    # every record with n >= 5 prints at least the final backtrack; total MFE <= every hit energy
+    assert (np.diff(hb)[lens >= 5] >= 1).all()
+    assert (res.total_mfe_dcal[rec_of_hit] <= tab["mfe_dcal"]).all()
+    assert (res.total_mfe_dcal <= 0).all()
+
+
+def test_full_size_properties_and_determinism(mf, oracle):
+    """BASELINE configs[1] at full size (10k loci, 300-600 nt, L=300): size-independent properties,
+    permutation invariance (checksum of per-record checksums) and oracle parity on a seeded sample."""
+    seqs = synth_loci(1001, 10000, "parity")
+    lens = np.array([len(s) for s in seqs])
+
+    def digest(res, order):
+        out = [None] * len(order)
+        for k, r in enumerate(order):
+            b, e = int(res.hit_begin[k]), int(res.hit_begin[k + 1])
+            h = hashlib.sha256()
+            h.update(res.hit_table[b:e][["start", "len", "mfe_dcal"]].tobytes())
+            if e > b:
+                o0 = int(res.hit_table[b]["ss_off"])
+                o1 = int(res.hit_table[e - 1]["ss_off"]) + int(res.hit_table[e - 1]["len"])
+                h.update(res.arena[o0:o1].tobytes())
+            h.update(int(res.total_mfe_dcal[k]).to_bytes(4, "little", signed=True))
+            out[r] = h.digest()
+        return hashlib.sha256(b"".join(out)).hexdigest()
+
+    with mf.fold(seqs, 300) as res:
+        _check_structure_properties(res, lens, 300)
+        d1 = digest(res, list(range(len(seqs))))
+        rng = np.random.default_rng(0)
+        for r in rng.choice(len(seqs), size=12, replace=False):
+            o = oracle.fold(seqs[r], 300)
+            assert res.hits(int(r)) == o["hits"] and res.total(int(r)) == o["total"]
+    perm = np.random.default_rng(1).permutation(len(seqs))
+    with mf.fold([seqs[k] for k in perm], 300) as res2:
+        assert digest(res2, perm.tolist()) == d1
+
+
+def test_device_resident_entry_counts_match(mf):
+    import torch
+    seqs = synth_loci(31, 200, "arabidopsis")
+    buf, off = mf.pack(seqs)
+    with mf.fold_packed(buf, off, 300) as host:
+        nh, nb = host.nhits, host.ss_bytes
+    d = torch.from_numpy(buf.copy()).cuda()
+    torch.cuda.synchronize()
+    with mf.fold_device(d.data_ptr(), off, 300, stream=torch.cuda.current_stream().cuda_stream) as dev:
+        assert dev.nhits == nh and dev.ss_bytes == nb and not dev.downloaded
+
+
+def test_multi_device_sharding_matches_single(mf):
+    import torch
+    import mir_prefer_b200 as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    seqs = synth_loci(41, 300, "parity")
+    with mf.fold(seqs, 300) as a, mp.MirFold(devices=list(range(torch.cuda.device_count()))) as m2, m2.fold(seqs, 300) as b:
+        assert b.stats["n_devices"] >= 2
+        for r in range(len(seqs)):
+            assert a.hits(r) == b.hits(r) and a.total(r) == b.total(r)
