@@ -229,43 +229,50 @@ __device__ __forceinline__ void dev_phase_a(const int *Mb, int *rD, StrideT NS, 
 }
 
 // ------------------------------------------------------------------------------------ K2 (shared-memory rings)
-#define MF_SLOTS 33   /* Cm ring: diagonals d-32 .. d */
+// Ring geometry: 33 slots hold Cm of diagonals d-32..d, slot 33 is all-INF.  Rows are RS = NS+32
+// words; diagonal d' is stored rotated by sk(d') = (11*d') & 31 words, which makes the bank of
+// Cm(p,q) for the loop (u,v) of a cell equal to (u - 11*(u+v) + const) mod 32.  With that skew the
+// 431 generic (u,v) terms split into 32 bank classes of <= 14 terms each: lane l owns class l and
+// the warp needs 14 conflict-free LDS per typed cell (DevParams::gen_us / gen_c).
+#define MF_SLOTS 33
 template <int NS>
 struct FillSmem {
-    static constexpr int cm_ints = (MF_SLOTS + 1) * NS;   // + one all-INF slot
-    static constexpr int dl_bytes = MF_SLOTS * NS;
-    static constexpr size_t bytes = (size_t)cm_ints * 4 + dl_bytes + 2 * (NS + 8) + 2 * NS + 16 * 32 * 4 + 64 + 16;
+    static constexpr int RS = NS + 32;
+    static constexpr int cm_ints = (MF_SLOTS + 1) * RS;
+    static constexpr int dl_bytes = MF_SLOTS * RS;
+    static constexpr size_t bytes = (size_t)cm_ints * 4 + dl_bytes + 2 * (NS + 8) + 2 * 2 * NS + 64 + 16;
 };
+__device__ __forceinline__ int dev_skew(int dp) { return (MF_SKEW_A * dp) & 31; }
 
 template <int NS, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) k_fill_smem(FillLaunch a)
 {
+    constexpr int RS = FillSmem<NS>::RS;
+    constexpr int NW = NT / 32, NWM = NW / 4, NWC = NW - NWM;       // fML/list warps, c warps
+    constexpr int CT = NWC * 32, MT = NWM * 32;
+    constexpr int INFOFF = MF_SLOTS * RS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    int *sCm = (int *)smem_raw;                                     // [34][NS]
-    unsigned char *sDl = (unsigned char *)(sCm + FillSmem<NS>::cm_ints);  // [33][NS]  AU - mismatchI + 70
-    unsigned char *sS = sDl + FillSmem<NS>::dl_bytes;               // [NS+8]
+    int *sCm = (int *)smem_raw;                                            // [34][RS]
+    unsigned char *sDl = (unsigned char *)(sCm + FillSmem<NS>::cm_ints);   // [33][RS]  AU - mismatchI + 70
+    unsigned char *sS = sDl + FillSmem<NS>::dl_bytes;                      // [NS+8]
     unsigned char *sS1 = sS + NS + 8;
-    unsigned short *sList = (unsigned short *)(sS1 + NS + 8);       // [NS]
-    int *sIlc = (int *)(sList + NS);                                // [16][32]
-    unsigned char *sPair = (unsigned char *)(sIlc + 16 * 32);       // [64]
-    __shared__ int sCount[2];
+    unsigned short *sList = (unsigned short *)(sS1 + NS + 8);              // [2][NS]
+    unsigned char *sPair = (unsigned char *)(sList + 2 * NS);              // [64]
+    __shared__ int sCount[3];
 
     const LocusDesc L = a.loci[blockIdx.x];
     const int n = L.n, Ls = L.Ls, dmax = L.dmax;
     const DevParams *__restrict__ P = a.P;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    constexpr int NW = NT / 32;
-    constexpr int INFSLOT = MF_SLOTS * NS;
 
     for (int k = tid; k < NS + 8; k += NT) {
         const unsigned char b = (k < n + 3) ? a.codes[L.seq_off + k] : 0;
         sS[k] = b & 7;
         sS1[k] = b >> 4;
     }
-    for (int k = tid; k < NS; k += NT) sCm[INFSLOT + k] = MF_INF;
-    for (int k = tid; k < 16 * 32; k += NT) sIlc[k] = P->ilc[k >> 5][k & 31];
+    for (int k = tid; k < RS; k += NT) sCm[INFOFF + k] = MF_INF;
     if (tid < 64) sPair[tid] = P->pair[tid];
-    if (tid < 2) sCount[tid] = 0;
+    if (tid < 3) sCount[tid] = 0;
 
     int *Cb = a.C + L.band_off;
     int *Mb = a.M + L.band_off;
@@ -273,104 +280,115 @@ __global__ void __launch_bounds__(NT, MINB) k_fill_smem(FillLaunch a)
     for (int k = tid; k < MF_RING_DML * NS; k += NT) rD[k] = MF_INF;
     __syncthreads();
 
-    // per-lane constants of the generic pass (INF = lane masked for this iteration)
-    int cst[16];
-    unsigned vmask = 0;
+    // per-lane constants of the generic pass
+    int cst[MF_GEN_ITERS];
 #pragma unroll
-    for (int it = 0; it < 16; it++) {
-        const int c = sIlc[it * 32 + lane];
-        if (c < MF_INF) vmask |= 1u << it;
+    for (int it = 0; it < MF_GEN_ITERS; it++) {
+        const int c = P->gen_c[it][lane];
         cst[it] = (c < MF_INF) ? c : 0;
     }
     const int nlB = lane + 2;                                          // bulge size handled by this lane
     const int cstB = (nlB <= 30) ? P->bulge[nlB] - 70 : 0;
 
-    // typed list of the first diagonal
+    // typed list of the first diagonal -> sList[0], sCount[4 % 3]
     if (dmax >= 4) {
         for (int i = tid + 1; i <= n - 4; i += NT) {
             const int t = (4 < Ls) ? sPair[sS[i] * 8 + sS[i + 4]] : 0;
-            if (t) sList[atomicAdd(&sCount[0], 1)] = (unsigned short)i;
-            else { Cb[i - 1] = MF_INF; sCm[(4 % MF_SLOTS) * NS + i - 1] = MF_INF; }
+            if (t) sList[atomicAdd(&sCount[1], 1)] = (unsigned short)i;
         }
     }
     __syncthreads();
 
-    for (int d = 4; d <= dmax; d++) {
-        if ((d - 4) % 5 == 0) {
-            dev_phase_a<NT>(Mb, rD, NS, n, d, min(d + 4, dmax), tid);
+    // iteration `it`: c warps fill c on diagonal it; fML warps fill fML on diagonal it-1 (which only
+    // the next iteration and later DML strips read) and build the typed list of diagonal it+1.
+    for (int it = 4; it <= dmax + 1; it++) {
+        if (it >= 5 && (it - 5) % 5 == 0 && it - 1 <= dmax) {
+            dev_phase_a<NT>(Mb, rD, NS, n, it - 1, min(it + 3, dmax), tid);   // DML strip [it-1, it+3]
             __syncthreads();
         }
-        // ---------------- phase C: c on diagonal d (typed cells only)
-        const int ntyped = sCount[d & 1];
-        if (tid == 0) sCount[(d + 1) & 1] = 0;
-        const int K = min(30, d - 6);
-        const int bslot = (d - 2) % MF_SLOTS;
-        const int dslot = d % MF_SLOTS;
-        int off[16];
+        if (wid < NWC) {
+            const int d = it;
+            if (d <= dmax) {
+                const int ntyped = sCount[d % 3];
+                const unsigned short *list = sList + (d & 1) * NS;
+                const int K = min(30, d - 6);
+                const int bslot = (d - 2) % MF_SLOTS;
+                const int drow = (d % MF_SLOTS) * RS + dev_skew(d);
+                // INF for the untyped cells of this diagonal (ring + band)
+                for (int i = tid + 1; i <= n - d; i += CT) {
+                    const int t = (d < Ls) ? sPair[sS[i] * 8 + sS[i + d]] : 0;
+                    if (!t) { sCm[drow + i - 1] = MF_INF; Cb[(d - 4) * NS + i - 1] = MF_INF; }
+                }
+                int off[MF_GEN_ITERS];
 #pragma unroll
-        for (int it = 0; it < 16; it++) {
-            int s, u;
-            if (it < 15) { if (lane <= it) { s = it; u = lane; } else { s = 30 - it; u = lane - it - 1; } }
-            else { s = 15; u = lane; }
-            int slot = bslot - s;
-            if (slot < 0) slot += MF_SLOTS;
-            off[it] = (s <= K && ((vmask >> it) & 1)) ? slot * NS + u : INFSLOT;
-        }
-        int offB1, offB2, offD1, offD2;
-        {
-            int slot = bslot - nlB;
-            if (slot < 0) slot += MF_SLOTS;
-            const bool ok = nlB <= K;                                   // K <= 30
-            offB1 = ok ? slot * NS + nlB : INFSLOT;                    // (u=nl, v=0): p = i+1+nl
-            offB2 = ok ? slot * NS : INFSLOT;                          // (u=0, v=nl): p = i+1
-            offD1 = ok ? slot * NS + nlB : 0;
-            offD2 = ok ? slot * NS : 0;
-        }
-        for (int c0 = wid * 32; c0 < ntyped; c0 += NW * 32) {
-            const int cnt = min(32, ntyped - c0);
-            int myG = MF_INF, myB = MF_INF;
-            for (int k = 0; k < cnt; k++) {
-                const int i = sList[c0 + k];
-                const int *w = sCm + i;
-                int g = MF_INF;
+                for (int k = 0; k < MF_GEN_ITERS; k++) {
+                    const int g = P->gen_us[k][lane];                  // u | s << 8 | valid << 16
+                    const int u = g & 0xff, s = (g >> 8) & 0xff;
+                    int slot = bslot - s;
+                    if (slot < 0) slot += MF_SLOTS;
+                    off[k] = ((g >> 16) && s <= K) ? slot * RS + dev_skew(d - 2 - s) + u : INFOFF;
+                }
+                int offB1, offB2, offD1, offD2;
+                {
+                    int slot = bslot - nlB;
+                    if (slot < 0) slot += MF_SLOTS;
+                    const bool ok = nlB <= K;                                   // K <= 30
+                    const int row = slot * RS + dev_skew(d - 2 - nlB);
+                    offB1 = ok ? row + nlB : INFOFF;                           // (u=nl, v=0): p = i+1+nl
+                    offB2 = ok ? row : INFOFF;                                 // (u=0, v=nl): p = i+1
+                    offD1 = ok ? row + nlB : 0;
+                    offD2 = ok ? row : 0;
+                }
+                const int per = (ntyped + NWC - 1) / NWC;
+                const int cend = min(ntyped, wid * per + per);
+                for (int c0 = wid * per; c0 < cend; c0 += 32) {
+                    const int cnt = min(32, cend - c0);
+                    int myG = MF_INF, myB = MF_INF;
+                    for (int k = 0; k < cnt; k++) {
+                        const int i = list[c0 + k];
+                        const int *w = sCm + i;
+                        int g = MF_INF;
 #pragma unroll
-                for (int it = 0; it < 16; it++) g = min(g, w[off[it]] + cst[it]);
-                int bb = min(w[offB1] + (int)sDl[offD1 + i], w[offB2] + (int)sDl[offD2 + i]) + cstB;
-                g = warp_min(g);
-                bb = warp_min(bb);
-                if (lane == k) { myG = g; myB = bb; }
+                        for (int q = 0; q < MF_GEN_ITERS; q++) g = min(g, w[off[q]] + cst[q]);
+                        int bb = min(w[offB1] + (int)sDl[offD1 + i], w[offB2] + (int)sDl[offD2 + i]) + cstB;
+                        g = warp_min(g);
+                        bb = warp_min(bb);
+                        if (lane == k) { myG = g; myB = bb; }
+                    }
+                    if (lane < cnt) {
+                        const int i = list[c0 + lane], j = i + d;
+                        const int t = sPair[sS[i] * 8 + sS[j]];
+                        const int si1 = sS1[i + 1], sj1 = sS1[j - 1];
+                        int best = myG + P->mismatchI[(t * 5 + si1) * 5 + sj1];
+                        best = min(best, myB + (t > 2 ? P->TerminalAU : 0));
+                        best = min(best, dev_cell_tail(P, sS, sS1, sPair, Cb, rD, NS, i, d, t, si1, sj1, K));
+                        const int tt = P->rtype[t];
+                        const int mm = P->mismatchI[(tt * 5 + sS1[j + 1]) * 5 + sS1[i - 1]];
+                        Cb[(d - 4) * NS + i - 1] = best;
+                        sCm[drow + i - 1] = best + mm;
+                        sDl[drow + i - 1] = (unsigned char)((tt > 2 ? P->TerminalAU : 0) - mm + 70);
+                    }
+                }
             }
-            if (lane < cnt) {
-                const int i = sList[c0 + lane], j = i + d;
-                const int t = sPair[sS[i] * 8 + sS[j]];
-                const int si1 = sS1[i + 1], sj1 = sS1[j - 1];
-                int best = myG + P->mismatchI[(t * 5 + si1) * 5 + sj1];
-                best = min(best, myB + (t > 2 ? P->TerminalAU : 0));
-                best = min(best, dev_cell_tail(P, sS, sS1, sPair, Cb, rD, NS, i, d, t, si1, sj1, K));
-                const int tt = P->rtype[t];
-                const int mm = P->mismatchI[(tt * 5 + sS1[j + 1]) * 5 + sS1[i - 1]];
-                Cb[(d - 4) * NS + i - 1] = best;
-                sCm[dslot * NS + i - 1] = best + mm;
-                sDl[dslot * NS + i - 1] = (unsigned char)((tt > 2 ? P->TerminalAU : 0) - mm + 70);
+        } else {
+            const int mt = tid - CT;
+            const int dm = it - 1;
+            if (dm >= 4) {
+                for (int i = mt + 1; i <= n - dm; i += MT)
+                    Mb[(dm - 4) * NS + i - 1] = dev_fml(P, sS, sS1, sPair, Cb, Mb, rD, NS, i, dm, Ls);
             }
-        }
-        __syncthreads();
-
-        // ---------------- phase M: fML on diagonal d; typed list + INF fill of diagonal d+1;
-        //                  reset of the DML ring slots of the next strip
-        const int ncell = n - d;
-        for (int i = tid + 1; i <= ncell; i += NT)
-            Mb[(d - 4) * NS + i - 1] = dev_fml(P, sS, sS1, sPair, Cb, Mb, rD, NS, i, d, Ls);
-        if (d + 1 <= dmax) {
-            const int dn = d + 1, nslot = dn % MF_SLOTS;
-            for (int i = tid + 1; i <= n - dn; i += NT) {
-                const int t = (dn < Ls) ? sPair[sS[i] * 8 + sS[i + dn]] : 0;
-                if (t) sList[atomicAdd(&sCount[dn & 1], 1)] = (unsigned short)i;
-                else { Cb[(dn - 4) * NS + i - 1] = MF_INF; sCm[nslot * NS + i - 1] = MF_INF; }
+            const int dn = it + 1;
+            if (mt == 0) sCount[(it + 2) % 3] = 0;
+            if (dn <= dmax) {
+                unsigned short *list = sList + (dn & 1) * NS;
+                for (int i = mt + 1; i <= n - dn; i += MT) {
+                    const int t = (dn < Ls) ? sPair[sS[i] * 8 + sS[i + dn]] : 0;
+                    if (t) list[atomicAdd(&sCount[dn % 3], 1)] = (unsigned short)i;
+                }
             }
-            if ((dn - 4) % 5 == 0) {
+            if ((it + 1 - 5) % 5 == 0 && it <= dmax) {   // next iteration runs the DML strip [it, it+4]
                 for (int s = 0; s < 5; s++)
-                    for (int i = tid; i < n; i += NT) rD[((dn + s) & (MF_RING_DML - 1)) * NS + i] = MF_INF;
+                    for (int i = mt; i < n; i += MT) rD[((it + s) & (MF_RING_DML - 1)) * NS + i] = MF_INF;
             }
         }
         __syncthreads();

@@ -173,6 +173,21 @@ void build_params(DevParams &P)
             }
             P.ilc[it][lane] = val;
         }
+    // skewed-ring schedule: lane = bank class (u - A*(u+v)) mod 32, <= MF_GEN_ITERS terms per lane
+    {
+        int fill[32] = {0};
+        for (int k = 0; k < MF_GEN_ITERS; k++)
+            for (int l = 0; l < 32; l++) { P.gen_c[k][l] = MF_INF; P.gen_us[k][l] = 0; }
+        for (int u = 0; u <= 30; u++)
+            for (int v = 0; u + v <= 30; v++) {
+                if (u == 0 || v == 0 || (u <= 2 && v <= 2)) continue;
+                const int cls = (((u - MF_SKEW_A * (u + v)) % 32) + 32) % 32;
+                const int k = fill[cls]++;
+                if (k >= MF_GEN_ITERS) { fprintf(stderr, "mirfold: skew schedule overflow\n"); abort(); }
+                P.gen_c[k][cls] = T99_internal_loop37[u + v] + std::min(maxninio, std::abs(u - v) * ninio);
+                P.gen_us[k][cls] = u | ((u + v) << 8) | (1 << 16);
+            }
+    }
     int m = 0;
     for (int u = 0; u <= 30; u++)
         for (int v = 0; v <= 30 - u; v++) { P.uv[m][0] = (unsigned char)u; P.uv[m][1] = (unsigned char)v; m++; }

@@ -15,6 +15,8 @@
 #define MF_INF 1000000
 #define MF_TURN 3
 #define MF_MAXLOOP 30
+#define MF_GEN_ITERS 14 /* generic interior-loop terms per lane in the skewed smem ring schedule */
+#define MF_SKEW_A 11    /* ring row rotation per diagonal: bank class of (u,v) = (u - 11*(u+v)) mod 32 */
 #define MF_MAX_SPAN 4096 /* hairpin-size table length; PRECURSOR_LEN is capped at 3000 (MP:168) */
 
 struct DevParams {
@@ -25,7 +27,9 @@ struct DevParams {
     int dangle5[40], dangle3[40];  // clamped <= 0
     int MLintern[8];
     int int11[8 * 8 * 25], int21[8 * 8 * 125], int22[8 * 8 * 625];
-    int ilc[16][32];               // generic interior-loop constants per (iteration, lane); INF = masked
+    int ilc[16][32];               // generic kernel: interior-loop constants per (iteration, lane); INF = masked
+    int gen_c[MF_GEN_ITERS][32];   // smem kernel: constant of the term lane l evaluates in iteration k (INF = none)
+    int gen_us[MF_GEN_ITERS][32];  //              its u | (u+v) << 8 | valid << 16
     int MLclosing, TerminalAU;
     short tetra[4096];             // tetraloop bonus by 2-bit packed 6-mer
     unsigned char pair[64];        // BP_pair[S_i*8+S_j]
