@@ -2,4 +2,8 @@
 from ._lib import MirfoldError, LIB_PATH  # noqa: F401
 from .fold import MirFold, FoldResult, parse_rnalfold_input, format_record, convert_sequence  # noqa: F401
 
-__all__ = ["MirFold", "FoldResult", "MirfoldError", "parse_rnalfold_input", "format_record", "convert_sequence"]
+from .structures import (structures_from_result, get_structures_next_extendregion, is_stem_loop, filter_ss,  # noqa: F401
+                         has_one_good_bifurcation, classify)
+
+__all__ = ["structures_from_result", "get_structures_next_extendregion", "is_stem_loop", "filter_ss",
+           "has_one_good_bifurcation", "classify", "MirFold", "FoldResult", "MirfoldError", "parse_rnalfold_input", "format_record", "convert_sequence"]

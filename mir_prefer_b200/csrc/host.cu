@@ -798,11 +798,52 @@ int mirfold_int_peak(mirfold_ctx *ctx, double *addmin_terms_per_s, double *dpx_t
     return MIRFOLD_OK;
 }
 
-int mirfold_duplex(mirfold_ctx *ctx, const char *, uint64_t, const mirfold_duplex_query *, uint64_t, mirfold_duplex_verdict *)
+int mirfold_duplex(mirfold_ctx *ctx, const char *ss_arena, uint64_t ss_bytes, const mirfold_duplex_query *queries,
+                   uint64_t nq, mirfold_duplex_verdict *verdicts)
 {
-    if (ctx) ctx->last_error = "mirfold_duplex: not built yet";
-    return MIRFOLD_ERR_ARG;
+    if (!ctx || (!ss_arena && ss_bytes) || (!queries && nq) || (!verdicts && nq)) return MIRFOLD_ERR_ARG;
+    if (nq == 0) return MIRFOLD_OK;
+    int maxlen = 1;
+    for (uint64_t k = 0; k < nq; k++) {
+        if (queries[k].ss_len < 0 || queries[k].ss_off + (uint64_t)queries[k].ss_len > ss_bytes) {
+            ctx->last_error = "mirfold_duplex: query structure outside the arena";
+            return MIRFOLD_ERR_ARG;
+        }
+        maxlen = std::max(maxlen, queries[k].ss_len);
+    }
+    if (maxlen > 32000) { ctx->last_error = "mirfold_duplex: structure longer than 32000"; return MIRFOLD_ERR_ARG; }
+    Device &D = ctx->devs[0];
+    cudaStream_t st = D.stream;
+    CK(cudaSetDevice(D.id));
+    CK(D.o_arena.ensure(ss_bytes + 16));
+    CK(D.scan_in.ensure(nq * sizeof(mirfold_duplex_query)));
+    CK(D.scan_out.ensure(nq * sizeof(mirfold_duplex_verdict)));
+    CK(cudaMemcpyAsync(D.o_arena.p, ss_arena, ss_bytes, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(D.scan_in.p, queries, nq * sizeof(mirfold_duplex_query), cudaMemcpyHostToDevice, st));
+    CK(launch_duplex(D.o_arena.as<char>(), D.scan_in.as<mirfold_duplex_query>(), nq, D.scan_out.as<mirfold_duplex_verdict>(),
+                     (maxlen + 7) & ~7, st));
+    CK(cudaMemcpyAsync(verdicts, D.scan_out.p, nq * sizeof(mirfold_duplex_verdict), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return MIRFOLD_OK;
 }
-const char *mirfold_duplex_fail_name(int) { return ""; }
+
+const char *mirfold_duplex_fail_name(int code)
+{
+    static const char *names[] = {"PASS",
+                                  "FAIL_STRUCTURE_MATCHED_BASES",
+                                  "FAIL_STRUCTURE_MATURE_NOT_IN_FOLD_REGION",
+                                  "FAIL_STRUCTURE_MATURE_NOT_IN_ONE_ARM",
+                                  "FAIL_STRUCTURE_MATURE_MATCH_SMALL_THAN_14",
+                                  "FAIL_STRUCTURE_MATURE_STAR_OVERLAP",
+                                  "FAIL_STRUCTURE_STAR_OUT_OF_FOLD_REGION",
+                                  "FAIL_STRUCTURE_STAR_NOT_IN_ONE_ARM",
+                                  "FAIL_STRUCTURE_TOO_MANY_BULGE_OR_LOOP",
+                                  "FAIL_STRUCTURE_MAX_BULGE_LARGE_THAN_2",
+                                  "FAIL_STRUCTURE_TOTAL_LOOP_SIZE_LARGER_THAN_5",
+                                  "FAIL_STRUCTURE_NUM_BULGE_MORE_THAN_2"};
+    if (code >= 0 && code < 12) return names[code];
+    if (code == 100) return "EXCEPTION_UNBALANCED_STRUCTURE";
+    return "";
+}
 
 }  // extern "C"

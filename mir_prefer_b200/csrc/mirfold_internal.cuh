@@ -116,3 +116,7 @@ cudaError_t launch_pack(const TraceBuffers &b, const unsigned long long *ss_off,
                         char *arena, int *out_start, int *out_len, int *out_energy, unsigned long long *out_ssoff,
                         cudaStream_t st);
 cudaError_t run_int_peak(cudaStream_t st, int sm_count, double *addmin, double *dpx);
+struct mirfold_duplex_query;
+struct mirfold_duplex_verdict;
+cudaError_t launch_duplex(const char *arena, const mirfold_duplex_query *qs, unsigned long long nq,
+                          mirfold_duplex_verdict *out, int maxlen, cudaStream_t st);

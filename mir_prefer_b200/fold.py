@@ -199,6 +199,46 @@ class MirFold:
             self._raise(rc)
         return c, m, f3
 
+    # ---- stage 3: duplex checks on the device --------------------------------------------------
+    def duplex(self, queries):
+        """get_maturestar_info() for many (structure, mature) pairs at once (miR_PREFeR.py:1876-1999).
+        queries: iterable of (ss, (m0, m1), foldstart, regionstart, regionend, strand) -- the reference's
+        argument order minus the redundant foldend.  Returns, per query, exactly what the reference
+        returns: the 9-tuple (star_start, star_end, fold_start, fold_end, star_ss, prime5, mature_ss,
+        total_dots, total_bps) in genome coordinates, or the FAIL_* string."""
+        queries = list(queries)
+        nq = len(queries)
+        if nq == 0:
+            return []
+        offs, parts, pos = {}, [], 0
+        qarr = (_lib.DuplexQuery * nq)()
+        for k, (ss, mature, foldstart, rs, re_, strand) in enumerate(queries):
+            if ss not in offs:
+                offs[ss] = pos
+                parts.append(ss)
+                pos += len(ss) + 1
+            q = qarr[k]
+            q.ss_off, q.ss_len, q.fold_start = offs[ss], len(ss), int(foldstart)
+            q.mature_start, q.mature_end = int(mature[0]), int(mature[1])
+            q.region_start, q.region_end, q.strand = int(rs), int(re_), ord(strand)
+        arena = ("\0".join(parts) + "\0").encode("ascii")
+        out = (_lib.DuplexVerdict * nq)()
+        rc = self._lib.mirfold_duplex(self._ctx, arena, len(arena), qarr, nq, out)
+        if rc != 0:
+            self._raise(rc)
+        res = []
+        for k, (ss, mature, foldstart, rs, re_, strand) in enumerate(queries):
+            v = out[k]
+            if v.code != 0:
+                name = self._lib.mirfold_duplex_fail_name(v.code).decode()
+                if v.code == 100:
+                    raise MirfoldError(-3, "duplex query %d: %s (the reference raises here)" % (k, name))
+                res.append(name)
+            else:
+                res.append((v.star_start, v.star_end, v.fold_start, v.fold_end, ss[v.star_ss_begin:v.star_ss_end],
+                            bool(v.prime5), ss[v.mature_ss_begin:v.mature_ss_end], v.total_dots, v.total_bps))
+        return res
+
     # ---- RNALfold CLI contract -------------------------------------------------------------
     def fold_text(self, text, span):
         """RNALfold-identical stdout for RNALfold-style stdin text (`RNALfold -L span`)."""

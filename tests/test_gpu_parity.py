@@ -122,7 +122,7 @@ def test_chunking_is_invisible(oracle):
 def _check_structure_properties(res, lens, L):
     hb = res.hit_begin
     tab = res.hit_table
-    assert (tab["len"] >= 1).all() and (tab["len"] <= L + 2).all()
+    assert (tab["len"] >= 1).all() and (tab["len"] <= L + 3).all()   # window touching the 3' end: up to L*+3 chars
     assert (tab["start"] >= 1).all()
     arena = res.arena
     # balanced brackets over the whole arena: every string is NUL-terminated, so a running depth
