@@ -150,7 +150,8 @@ def test_full_size_properties_and_determinism(mf, oracle):
         for k, r in enumerate(order):
             b, e = int(res.hit_begin[k]), int(res.hit_begin[k + 1])
             h = hashlib.sha256()
-            h.update(res.hit_table[b:e][["start", "len", "mfe_dcal"]].tobytes())
+            t = res.hit_table[b:e]   # explicit columns: a multi-field view would drag ss_off along in tobytes()
+            h.update(np.stack([t["start"], t["len"], t["mfe_dcal"]]).astype("<i4").tobytes())
             if e > b:
                 o0 = int(res.hit_table[b]["ss_off"])
                 o1 = int(res.hit_table[e - 1]["ss_off"]) + int(res.hit_table[e - 1]["len"])
