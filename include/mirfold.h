@@ -37,6 +37,12 @@ extern "C" {
  * 1.8.5, dangles=1, 37 C, tetraloop bonus on (what `RNALfold -L n` uses by default). */
 #define MIRFOLD_PARAMSET_DEFAULT "vienna-1.8.5-d1"
 
+/* mirfold_fold flags.  The band fill normally runs a kernel that keeps its interior-loop window as
+ * 16-bit values and transparently redoes any locus whose energies leave that range (below
+ * -320 kcal/mol inside one window) with the 32-bit kernel; MIRFOLD_FLAG_WIDE forces the 32-bit kernel
+ * for every locus.  Results are identical either way. */
+#define MIRFOLD_FLAG_WIDE 1u
+
 typedef struct mirfold_ctx mirfold_ctx;
 
 /* One printed RNALfold hairpin line: "<ss> (<mfe/100>) <start>".  Replaces one line of the
@@ -106,8 +112,8 @@ int mirfold_fold_device(mirfold_ctx *ctx, const void *d_seqs, const void *d_seq_
 /* Debug/test hook: fill + f3 for ONE sequence and copy the band matrices back in the oracle's
  * [i][d] layout (row stride W = min(L,n)+6, rows 0..n+1, INF=1000000 where not computed).
  * c/m must hold (n+2)*W ints, f3 must hold n+4 ints. */
-int mirfold_debug_matrices(mirfold_ctx *ctx, const char *seq, uint32_t n, int span_L, int32_t *c,
-                           int32_t *m, int32_t *f3);
+int mirfold_debug_matrices(mirfold_ctx *ctx, const char *seq, uint32_t n, int span_L, uint32_t flags,
+                           int32_t *c, int32_t *m, int32_t *f3);
 
 void mirfold_free_result(mirfold_result *res);
 

@@ -77,7 +77,7 @@ def load():
     lib.mirfold_fold_device.argtypes = [vp, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.c_uint32, C.c_int,
                                         C.c_uint32, C.c_void_p, C.POINTER(C.POINTER(Result))]
     lib.mirfold_fold_device.restype = C.c_int
-    lib.mirfold_debug_matrices.argtypes = [vp, C.c_char_p, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.mirfold_debug_matrices.argtypes = [vp, C.c_char_p, C.c_uint32, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.mirfold_debug_matrices.restype = C.c_int
     lib.mirfold_free_result.argtypes = [C.POINTER(Result)]
     lib.mirfold_free_result.restype = None

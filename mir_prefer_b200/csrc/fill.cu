@@ -18,6 +18,8 @@
 //     with redux.sync.  Bulges reuse the ring through a byte ring of (AU - mismatch) deltas.
 //   * the 7 table-driven two-loops (stack, 1-nt bulges, 1x1, 1x2, 2x1, 2x2), the hairpin and the
 //     d1 multiloop closing are evaluated lane-per-cell for 32 typed cells at a time.
+#include <cstdlib>
+#include <cstring>
 #include "mirfold_internal.cuh"
 
 // ------------------------------------------------------------------------------------ K1
@@ -260,6 +262,7 @@ __global__ void __launch_bounds__(NT, MINB) k_fill_smem(FillLaunch a)
     unsigned char *sPair = (unsigned char *)(sList + 2 * NS);              // [64]
     __shared__ int sCount[3];
 
+    if (a.flags && !a.flags[blockIdx.x]) return;   // only loci the 16-bit kernel flagged
     const LocusDesc L = a.loci[blockIdx.x];
     const int n = L.n, Ls = L.Ls, dmax = L.dmax;
     const DevParams *__restrict__ P = a.P;
@@ -395,6 +398,199 @@ __global__ void __launch_bounds__(NT, MINB) k_fill_smem(FillLaunch a)
     }
 }
 
+
+// ------------------------------------------------------------------------------------ K2 (narrow: 16-bit pair ring)
+// Same wavefront as k_fill_smem, but the interior-loop window is kept as 16-bit values with two
+// adjacent diagonals per 32-bit word:  sG = c + mismatchI (generic loops), sB = c + AU (bulges).
+// Pair pp = d'>>1 lives in slot pp % 17, rotated by (17 pp) & 31 words; lane l owns the word-terms of
+// bank class l (DevParams::s16_*), so a typed cell costs 10 conflict-free LDS + 10 VIADDMNMX.S16x2 per
+// lane (8 generic, 2 bulge), one packed combine and one redux.  Exact while c > MF16_GUARD; otherwise
+// the locus is flagged for the 32-bit kernel.
+// shared-memory load from an absolute 32-bit shared address (volatile: never hoisted or merged)
+__device__ __forceinline__ unsigned dev_lds(unsigned addr)
+{
+    unsigned w;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(addr));
+    return w;
+}
+
+template <int NS>
+struct Fill16Smem {
+    static constexpr int RS = NS + 32;
+    static constexpr int ring_words = (MF16_NPS + 1) * RS;   // + one all-INF row
+    static constexpr size_t bytes = (size_t)2 * ring_words * 4 + (size_t)2 * NS * 4 + 200 * 4 + 32 * 4 + 2 * (NS + 8) + 64 + 16;
+};
+
+__device__ __forceinline__ int dev_row16(int d, int m, int RS)
+{   // word offset of pair slot m (relative to diagonal d) inside a ring
+    const int pp = ((d - 2) >> 1) - m;
+    return pp < 0 ? MF16_NPS * RS : (pp % MF16_NPS) * RS + ((MF16_SKEW * pp) & 31);
+}
+__device__ __forceinline__ void dev_ring16_put(unsigned int *ring, int RS, int d, int x, int v)
+{
+    const int pp = d >> 1;
+    unsigned short *w = (unsigned short *)(ring + (pp % MF16_NPS) * RS + ((MF16_SKEW * pp) & 31) + x);
+    w[d & 1] = (unsigned short)v;
+}
+
+template <int NS, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) k_fill_s16(FillLaunch a)
+{
+    constexpr int RS = Fill16Smem<NS>::RS, RW = Fill16Smem<NS>::ring_words;
+    constexpr int NW = NT / 32, NWM = NW / 4, NWC = NW - NWM;
+    constexpr int CT = NWC * 32, MT = NWM * 32;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned int *sG = (unsigned int *)smem_raw;              // [18][RS]
+    unsigned int *sB = sG + RW;                               // [18][RS]
+    unsigned int *sList = sB + RW;                            // [2][NS]  i*4 | (AU - mismatchI + bias) << 16
+    int *sMM = (int *)(sList + 2 * NS);                       // mismatchI[200]
+    int *sRow = sMM + 200;                                    // [2][16] pair-slot row offsets of diagonal d (by parity)
+    unsigned char *sS = (unsigned char *)(sRow + 32);         // [NS+8]
+    unsigned char *sS1 = sS + NS + 8;
+    unsigned char *sPair = sS1 + NS + 8;                      // [64]
+    __shared__ int sCount[3];
+    __shared__ int sFlag;
+
+    const LocusDesc L = a.loci[blockIdx.x];
+    const int n = L.n, Ls = L.Ls, dmax = L.dmax;
+    const DevParams *__restrict__ P = a.P;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int AUp = P->TerminalAU;
+
+    for (int k = tid; k < NS + 8; k += NT) {
+        const unsigned char b = (k < n + 3) ? a.codes[L.seq_off + k] : 0;
+        sS[k] = b & 7;
+        sS1[k] = b >> 4;
+    }
+    for (int k = tid; k < 2 * RW; k += NT) sG[k] = MF16_INF2;
+    for (int k = tid; k < 200; k += NT) sMM[k] = P->mismatchI[k];
+    if (tid < 64) sPair[tid] = P->pair[tid];
+    if (tid < 3) sCount[tid] = 0;
+    if (tid == 0) sFlag = 0;
+    if (tid < 16) sRow[tid] = dev_row16(4, tid, RS);
+
+    int *Cb = a.C + L.band_off;
+    int *Mb = a.M + L.band_off;
+    int *rD = a.ring + L.ring_off;   // [MF_RING_DML][NS]
+    for (int k = tid; k < MF_RING_DML * NS; k += NT) rD[k] = MF_INF;
+    __syncthreads();
+
+    // typed list / untyped INF of the first diagonal
+    if (dmax >= 4) {
+        for (int i = tid + 1; i <= n - 4; i += NT) {
+            const int t = (4 < Ls) ? sPair[sS[i] * 8 + sS[i + 4]] : 0;
+            if (t) {
+                const int dl = (t > 2 ? AUp : 0) - sMM[(t * 5 + sS1[i + 1]) * 5 + sS1[i + 3]] + MF16_DBIAS;
+                sList[atomicAdd(&sCount[1], 1)] = (unsigned)(i * 4) | ((unsigned)dl << 16);
+            } else Cb[i - 1] = MF_INF;   // ring halves already hold INF
+        }
+    }
+    __syncthreads();
+
+    const unsigned smem_base = (unsigned)__cvta_generic_to_shared(smem_raw);
+
+    for (int it = 4; it <= dmax + 1; it++) {
+        if (it >= 5 && (it - 5) % 5 == 0 && it - 1 <= dmax) {
+            dev_phase_a<NT>(Mb, rD, NS, n, it - 1, min(it + 3, dmax), tid);   // DML strip [it-1, it+3]
+            __syncthreads();
+        }
+        if (wid < NWC) {
+            const int d = it;
+            if (d <= dmax) {
+                const int par = d & 1;
+                const int ntyped = sCount[d % 3];
+                const unsigned int *list = sList + par * NS;
+                const int K = min(30, d - 6);
+                // per-lane word-term addresses (bytes, shared window) and packed constants
+                unsigned off[MF16_NQ], cst[MF16_NQ], mk[MF16_NMK];
+#pragma unroll
+                for (int q = 0; q < MF16_NQ; q++) {
+                    const unsigned td = P->s16_td[par][q][lane];
+                    const int m = td & 15, xo = (td >> 4) & 63;
+                    const int row = (td >> 11) ? MF16_NPS * RS : sRow[par * 16 + m];
+                    off[q] = smem_base + (unsigned)(((td >> 10) & 1) * RW + row + xo) * 4u;
+                    asm("" : "+r"(off[q]));   // keep the byte address as one register (no re-association in the cell loop)
+                    cst[q] = P->s16_cst[par][q][lane];
+                }
+#pragma unroll
+                for (int q = 0; q < MF16_NMK; q++) mk[q] = P->s16_mk[par][q][lane];
+
+                const int per = (ntyped + NWC - 1) / NWC;
+                const int cend = min(ntyped, wid * per + per);
+                for (int c0 = wid * per; c0 < cend; c0 += 32) {
+                    const int cnt = min(32, cend - c0);
+                    int my = MF16_INF;
+                    for (int k = 0; k < cnt; k++) {
+                        const unsigned e = list[c0 + k];
+                        const unsigned i4 = e & 0xffffu;
+                        unsigned accG = MF16_INF2, accB = MF16_INF2;
+#pragma unroll
+                        for (int q = 0; q < MF16_NQG; q++) {
+                            unsigned w = dev_lds(off[q] + i4);
+                            if (q < MF16_NMG) w = (w & mk[q]) | (~mk[q] & MF16_INF2);
+                            accG = __viaddmin_s16x2(w, cst[q], accG);
+                        }
+#pragma unroll
+                        for (int q = 0; q < MF16_NQB; q++) {
+                            unsigned w = dev_lds(off[MF16_NQG + q] + i4);
+                            w = (w & mk[MF16_NMG + q]) | (~mk[MF16_NMG + q] & MF16_INF2);
+                            accB = __viaddmin_s16x2(w, cst[MF16_NQG + q], accB);
+                        }
+                        const unsigned dl2 = __byte_perm(e, 0, 0x3232);              // (dl, dl)
+                        const unsigned acc = __viaddmin_s16x2(accB, dl2, accG);      // relative to the outer mismatch
+                        int v = min((int)(short)(acc & 0xffffu), (int)acc >> 16);
+                        v = warp_min(v);
+                        if (lane == k) my = v;
+                    }
+                    if (lane < cnt) {
+                        const int i = (int)(list[c0 + lane] & 0xffffu) >> 2, j = i + d;
+                        const int t = sPair[sS[i] * 8 + sS[j]];
+                        const int si1 = sS1[i + 1], sj1 = sS1[j - 1];
+                        int best = (my < MF16_VALID) ? my + sMM[(t * 5 + si1) * 5 + sj1] : MF_INF;
+                        best = min(best, dev_cell_tail(P, sS, sS1, sPair, Cb, rD, NS, i, d, t, si1, sj1, K));
+                        const int tt = P->rtype[t];
+                        const int mm = sMM[(tt * 5 + sS1[j + 1]) * 5 + sS1[i - 1]];
+                        Cb[(d - 4) * NS + i - 1] = best;
+                        if (best < MF16_GUARD) sFlag = 1;
+                        dev_ring16_put(sG, RS, d, i - 1, max(best + mm, -32768));
+                        dev_ring16_put(sB, RS, d, i - 1, max(best + (tt > 2 ? AUp : 0), -32768));
+                    }
+                }
+            }
+        } else {
+            const int mt = tid - CT;
+            const int dm = it - 1;
+            if (dm >= 4) {
+                for (int i = mt + 1; i <= n - dm; i += MT)
+                    Mb[(dm - 4) * NS + i - 1] = dev_fml(P, sS, sS1, sPair, Cb, Mb, rD, NS, i, dm, Ls);
+            }
+            const int dn = it + 1;
+            if (mt == 0) sCount[(it + 2) % 3] = 0;
+            if (dn <= dmax) {
+                unsigned int *list = sList + (dn & 1) * NS;
+                for (int i = mt + 1; i <= n - dn; i += MT) {
+                    const int t = (dn < Ls) ? sPair[sS[i] * 8 + sS[i + dn]] : 0;
+                    if (t) {
+                        const int dl = (t > 2 ? AUp : 0) - sMM[(t * 5 + sS1[i + 1]) * 5 + sS1[i + dn - 1]] + MF16_DBIAS;
+                        list[atomicAdd(&sCount[dn % 3], 1)] = (unsigned)(i * 4) | ((unsigned)dl << 16);
+                    } else {
+                        dev_ring16_put(sG, RS, dn, i - 1, MF16_INF);
+                        dev_ring16_put(sB, RS, dn, i - 1, MF16_INF);
+                        Cb[(dn - 4) * NS + i - 1] = MF_INF;
+                    }
+                }
+                if (mt < 16) sRow[(dn & 1) * 16 + mt] = dev_row16(dn, mt, RS);
+            }
+            if ((it + 1 - 5) % 5 == 0 && it <= dmax) {   // next iteration runs the DML strip [it, it+4]
+                for (int s = 0; s < 5; s++)
+                    for (int i = mt; i < n; i += MT) rD[((it + s) & (MF_RING_DML - 1)) * NS + i] = MF_INF;
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0 && sFlag) a.flags[blockIdx.x] = 1;
+}
+
 // ------------------------------------------------------------------------------------ K2 (generic: any n)
 // Same algorithm with the Cm window in a global-memory ring (for loci longer than the largest
 // shared-memory bucket).  Dynamic smem: sS[npad] | sS1[npad] | pairtab[64] | list[n] (int)
@@ -493,20 +689,38 @@ __global__ void __launch_bounds__(NT) k_fill_generic(FillLaunch a)
 }
 
 template <int NS, int NT, int MINB>
+static cudaError_t configure_fill_bucket()
+{
+    cudaError_t e = cudaFuncSetAttribute(k_fill_smem<NS, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FillSmem<NS>::bytes);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_fill_s16<NS, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Fill16Smem<NS>::bytes);
+}
+// function attributes are per device: called once per device of a context (mirfold_open)
+cudaError_t fill_configure_device()
+{
+    cudaError_t e;
+    if ((e = configure_fill_bucket<608, 512, 2>()) != cudaSuccess) return e;
+    if ((e = configure_fill_bucket<352, 384, 3>()) != cudaSuccess) return e;
+    if ((e = configure_fill_bucket<160, 256, 4>()) != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_fill_generic<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+}
+
+template <int NS, int NT, int MINB>
 static cudaError_t launch_fill_bucket(const FillLaunch &a, int first, int count, cudaStream_t st)
 {
     if (count <= 0) return cudaSuccess;
-    static bool configured = false;
-    const size_t smem = FillSmem<NS>::bytes;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_fill_smem<NS, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    const size_t smem = FillSmem<NS>::bytes, smem16 = Fill16Smem<NS>::bytes;
     FillLaunch b = a;
     b.loci = a.loci + first;
     b.nloci = count;
-    k_fill_smem<NS, NT, MINB><<<count, NT, smem, st>>>(b);
+    if (a.force_wide) b.flags = nullptr;
+    else {
+        b.flags = a.flags + first;
+        k_fill_s16<NS, NT, MINB><<<count, NT, smem16, st>>>(b);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    k_fill_smem<NS, NT, MINB><<<count, NT, smem, st>>>(b);   // 32-bit kernel: all loci if forced, else only flagged ones
     return cudaGetLastError();
 }
 
@@ -522,12 +736,7 @@ cudaError_t launch_fill(const FillLaunch &a, cudaStream_t st)
         constexpr int NT = 512;
         const int npad = (a.max_n + 3 + 15) & ~15;
         const size_t smem = (size_t)2 * npad + 64 + (size_t)a.max_n * sizeof(int) + 16;
-        static size_t configured = 0;
-        if (smem > 48 * 1024 && smem > configured) {
-            e = cudaFuncSetAttribute(k_fill_generic<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
-            configured = smem;
-        }
+        if (smem > 200 * 1024) return cudaErrorInvalidValue;   // n > ~33 000 nt
         FillLaunch b = a;
         b.loci = a.loci + a.bucket_first[0];
         b.nloci = ng;
@@ -541,8 +750,108 @@ cudaError_t launch_fill(const FillLaunch &a, cudaStream_t st)
 }
 
 // ------------------------------------------------------------------------------------ K3
-// f3 scan (A.3, "RLF Lfold.c:355-398"): one warp per locus, lanes over j, rows sequential.
+// f3 scan (A.3, "RLF Lfold.c:355-398").  One warp per locus; rows are taken in blocks of 32 from the
+// 3' end.  f3(i) = min(f3(i+1), min_j term(i,j)) where term(i,j) reads f3(j+1), f3(j+2) with
+// j >= i+4, so for a block [ilo, ihi] every term with span d >= 31 only reads rows above the block:
+//   phase P: lane = row, loop over d = 31..L* -- all loads of the diagonal-major band are coalesced
+//            (32 consecutive rows of one diagonal = 128 B) and f3/code operands slide in registers;
+//   phase S: rows sequential, lane = d (4..30) with the f3 window f3(i+1..i+32) kept in registers
+//            and shifted by one lane per row; lane 31 takes the j == n boundary term.
+__device__ __forceinline__ int dev_f3_term(const unsigned char *sPair, const int *sD3, const int *sD5, int AUp,
+                                           int si, int s1i, int si1, int sj, int s1j1, int d, int Ls,
+                                           int cA, int cB, int f1, int f2)
+{
+    int best = MF_INF;
+    int t = (d < Ls) ? sPair[si * 8 + sj] : 0;
+    if (t) {
+        const int e = cA + (t > 2 ? AUp : 0);
+        best = min(e + f1, e + sD3[t * 5 + s1j1] + f2);
+    }
+    t = (d - 1 >= 4) ? sPair[si1 * 8 + sj] : 0;
+    if (t) {
+        const int e = cB + sD5[t * 5 + s1i] + (t > 2 ? AUp : 0);
+        best = min(best, min(e + f1, e + sD3[t * 5 + s1j1] + f2));
+    }
+    return best;
+}
+
 __global__ void __launch_bounds__(128) k_f3(const LocusDesc *__restrict__ loci, int nloci,
+                                            const unsigned char *__restrict__ codes, const int *__restrict__ Call,
+                                            int *__restrict__ Fall, const DevParams *__restrict__ P)
+{
+    __shared__ unsigned char sPair[64];
+    __shared__ int sD3[40], sD5[40];
+    if (threadIdx.x < 64) sPair[threadIdx.x] = P->pair[threadIdx.x];
+    if (threadIdx.x < 40) { sD3[threadIdx.x] = P->dangle3[threadIdx.x]; sD5[threadIdx.x] = P->dangle5[threadIdx.x]; }
+    __syncthreads();
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= nloci) return;
+    const LocusDesc L = loci[w];
+    const int n = L.n, Ls = L.Ls, NS = L.stride;
+    const unsigned char *__restrict__ cd = codes + L.seq_off;
+    const int *__restrict__ C = Call + L.band_off;
+    int *F = Fall + L.seq_off;
+    const int AUp = P->TerminalAU;
+    constexpr int DS = 31;   // first span of phase P
+    for (int ihi = n - 4; ihi >= 1; ihi -= 32) {
+        const int ilo = max(1, ihi - 31);
+        // ---- phase P
+        int gout = MF_INF;
+        {
+            const int i = ilo + lane;
+            if (i <= ihi) {
+                const int dend = min(Ls, n - 1 - i);
+                if (dend >= DS) {
+                    const int ci = cd[i], si = ci & 7, s1i = ci >> 4, si1 = cd[i + 1] & 7;
+                    int j = i + DS;
+                    int cj = cd[j], f1 = F[j + 1];
+                    const int *pa = C + (DS - 4) * NS + (i - 1);   // C(i, i+d)
+                    for (int d = DS; d <= dend; d++, j++, pa += NS) {
+                        const int cj1 = cd[j + 1], f2 = F[j + 2];
+                        const int cA = pa[0], cB = pa[1 - NS];      // C(i+1, j) sits one diagonal down, one row up
+                        gout = min(gout, dev_f3_term(sPair, sD3, sD5, AUp, si, s1i, si1, cj & 7, cj1 >> 4, d, Ls, cA, cB, f1, f2));
+                        cj = cj1; f1 = f2;
+                    }
+                }
+            }
+        }
+        // ---- phase S
+        int Fw;
+        {
+            const int k = ihi + 1 + lane;
+            Fw = (k <= n + 2) ? F[k] : 0;
+        }
+        for (int i = ihi; i >= ilo; i--) {
+            const int d = lane, j = i + d;
+            const int f2 = __shfl_down_sync(0xffffffffu, Fw, 1);
+            const int ci = cd[i], si = ci & 7, s1i = ci >> 4, si1 = cd[i + 1] & 7;
+            int best = MF_INF;
+            if (d >= 4 && d < DS && d <= Ls && j <= n - 1) {
+                const int cA = C[(d - 4) * NS + (i - 1)];
+                const int cB = (d >= 5) ? C[(d - 5) * NS + i] : MF_INF;
+                best = dev_f3_term(sPair, sD3, sD5, AUp, si, s1i, si1, cd[j] & 7, cd[j + 1] >> 4, d, Ls, cA, cB, Fw, f2);
+            }
+            if (lane == 31 && n <= i + Ls) {   // j == n: no f3 / dangle3 terms
+                const int dn = n - i, sj = cd[n] & 7;
+                int t = (dn < Ls) ? sPair[si * 8 + sj] : 0;
+                if (t) best = min(best, C[(dn - 4) * NS + (i - 1)] + (t > 2 ? AUp : 0));
+                t = (dn - 1 >= 4) ? sPair[si1 * 8 + sj] : 0;
+                if (t) best = min(best, C[(dn - 5) * NS + i] + sD5[t * 5 + s1i] + (t > 2 ? AUp : 0));
+            }
+            best = warp_min(best);
+            const int g = __shfl_sync(0xffffffffu, gout, i - ilo);
+            const int fnext = __shfl_sync(0xffffffffu, Fw, 0);   // f3(i+1)
+            const int fi = min(fnext, min(best, g));
+            if (lane == 0) F[i] = fi;
+            Fw = __shfl_up_sync(0xffffffffu, Fw, 1);
+            if (lane == 0) Fw = fi;
+        }
+        __syncwarp();
+    }
+}
+
+// previous one-warp-per-locus version (strided band reads); kept selectable with MIRFOLD_F3=v1 for A/B runs
+__global__ void __launch_bounds__(128) k_f3_v1(const LocusDesc *__restrict__ loci, int nloci,
                                             const unsigned char *__restrict__ codes, const int *__restrict__ Call,
                                             int *__restrict__ Fall, const DevParams *__restrict__ P)
 {
@@ -592,6 +901,8 @@ cudaError_t launch_f3(const LocusDesc *loci, int nloci, const unsigned char *cod
 {
     if (nloci == 0) return cudaSuccess;
     const int warps_per_block = 4;
-    k_f3<<<(nloci + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(loci, nloci, codes, C, F, P);
+    static const bool v1 = getenv("MIRFOLD_F3") && !strcmp(getenv("MIRFOLD_F3"), "v1");
+    if (v1) k_f3_v1<<<(nloci + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(loci, nloci, codes, C, F, P);
+    else k_f3<<<(nloci + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(loci, nloci, codes, C, F, P);
     return cudaGetLastError();
 }

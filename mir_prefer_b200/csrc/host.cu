@@ -80,14 +80,14 @@ struct Device {
     DevParams *dP = nullptr;
     size_t mem_budget = 0;
     // pooled buffers
-    DBuf raw, loci, codes, F, C, M, ring, tbcount, tbbase, listoff, startlist, scan_in, scan_out, scan_tmp;
+    DBuf raw, loci, codes, F, C, M, ring, fillflags, tbcount, tbbase, listoff, startlist, scan_in, scan_out, scan_tmp;
     DBuf slots, tblen, tbstart, tblocus, tbflag, tbenergy, stackscr, fail, ssoff, hitidx;
     DBuf o_start, o_len, o_energy, o_ssoff, o_arena;
     HBuf h_raw, h_loci, h_listoff, h_small, h_out;
     cudaEvent_t ev[12] = {};
     void release()
     {
-        DBuf *all[] = {&raw, &loci, &codes, &F, &C, &M, &ring, &tbcount, &tbbase, &listoff, &startlist, &scan_in,
+        DBuf *all[] = {&raw, &loci, &codes, &F, &C, &M, &ring, &fillflags, &tbcount, &tbbase, &listoff, &startlist, &scan_in,
                        &scan_out, &scan_tmp, &slots, &tblen, &tbstart, &tblocus, &tbflag, &tbenergy, &stackscr, &fail,
                        &ssoff, &hitidx, &o_start, &o_len, &o_energy, &o_ssoff, &o_arena};
         for (DBuf *b : all) b->release();
@@ -121,6 +121,60 @@ struct ResultOwner {  // lives right behind the public struct
     HBuf arena;               // single-device fast path: pinned arena moved from the Partial
     std::vector<char> arena_v;  // multi-device path: concatenated
 };
+
+// ------------------------------------------------------------------ narrow-kernel schedule
+// Word-terms of the 16-bit pair ring (see k_fill_s16).  For a cell on diagonal d, pair slot m
+// (0..15) holds the inner diagonals of loop sizes (s_lo, s_hi) = (2m, 2m-1) for even d and
+// (2m+1, 2m) for odd d.  A word-term is (ring, m, x-offset): generic terms read Cm at row offset u
+// for both sizes; bulges read c+AU at offset 0 (5' side unpaired = 0) as pairs and at offset s
+// (3' side) as single halves.  The bank class of a word-term is (xoff - 17 m) mod 32 and lane = class,
+// so every unrolled iteration is one conflict-free LDS.
+void build_s16_schedule(DevParams &P)
+{
+    const int ninio = T99_F_ninio37[2], maxninio = T99_MAX_NINIO;
+    struct Term { int m, xo, ring, clo, chi; bool vlo, vhi; };
+    auto generic_ok = [](int s, int u) { const int v = s - u; return s >= 0 && s <= 30 && u >= 1 && v >= 1 && !(u <= 2 && v <= 2); };
+    auto gconst = [&](int s, int u) { return T99_internal_loop37[s] + std::min(maxninio, std::abs(2 * u - s) * ninio); };
+    for (int par = 0; par < 2; par++) {
+        std::vector<Term> G[32], B[32];
+        for (int m = 0; m < 16; m++) {
+            const int slo = par ? 2 * m + 1 : 2 * m, shi = par ? 2 * m : 2 * m - 1;
+            for (int u = 1; u <= 30; u++) {
+                const bool a = generic_ok(slo, u), b = generic_ok(shi, u);
+                if (a || b) G[((u - MF16_SKEW * m) % 32 + 32) % 32].push_back({m, u, 0, a ? gconst(slo, u) : 0, b ? gconst(shi, u) : 0, a, b});
+            }
+            const bool a = slo >= 2 && slo <= 30, b = shi >= 2 && shi <= 30;
+            if (a || b)
+                B[((0 - MF16_SKEW * m) % 32 + 32) % 32].push_back({m, 0, 1, a ? T99_bulge37[slo] - MF16_DBIAS : 0, b ? T99_bulge37[shi] - MF16_DBIAS : 0, a, b});
+            if (a) B[((slo - MF16_SKEW * m) % 32 + 32) % 32].push_back({m, slo, 1, T99_bulge37[slo] - MF16_DBIAS, 0, true, false});
+            if (b) B[((shi - MF16_SKEW * m) % 32 + 32) % 32].push_back({m, shi, 1, 0, T99_bulge37[shi] - MF16_DBIAS, false, true});
+        }
+        for (int lane = 0; lane < 32; lane++) {
+            std::stable_sort(G[lane].begin(), G[lane].end(), [](const Term &x, const Term &y) { return (x.vlo && x.vhi) < (y.vlo && y.vhi); });
+            int nmask = 0;
+            for (const Term &t : G[lane]) nmask += !(t.vlo && t.vhi);
+            if ((int)G[lane].size() > MF16_NQG || (int)B[lane].size() > MF16_NQB || nmask > MF16_NMG) {
+                fprintf(stderr, "mirfold: 16-bit schedule overflow (par %d lane %d: %zu generic, %zu bulge, %d masked)\n", par, lane,
+                        G[lane].size(), B[lane].size(), nmask);
+                abort();
+            }
+            auto put = [&](int q, const Term *t) {
+                if (t) {
+                    P.s16_td[par][q][lane] = (unsigned)t->m | ((unsigned)t->xo << 4) | ((unsigned)t->ring << 10);
+                    P.s16_cst[par][q][lane] = ((unsigned)t->clo & 0xffffu) | ((unsigned)t->chi << 16);
+                } else {   // no term: read the all-INF row at a lane-private bank
+                    P.s16_td[par][q][lane] = (unsigned)lane << 4 | 1u << 11;
+                    P.s16_cst[par][q][lane] = 0;
+                }
+                const unsigned mk = t ? ((t->vlo ? 0xffffu : 0u) | (t->vhi ? 0xffff0000u : 0u)) : 0xffffffffu;
+                if (q < MF16_NMG) P.s16_mk[par][q][lane] = mk;
+                else if (q >= MF16_NQG) P.s16_mk[par][MF16_NMG + q - MF16_NQG][lane] = mk;
+            };
+            for (int q = 0; q < MF16_NQG; q++) put(q, q < (int)G[lane].size() ? &G[lane][q] : nullptr);
+            for (int q = 0; q < MF16_NQB; q++) put(MF16_NQG + q, q < (int)B[lane].size() ? &B[lane][q] : nullptr);
+        }
+    }
+}
 
 // ------------------------------------------------------------------ parameter set (a10)
 void build_params(DevParams &P)
@@ -191,6 +245,7 @@ void build_params(DevParams &P)
     int m = 0;
     for (int u = 0; u <= 30; u++)
         for (int v = 0; v <= 30 - u; v++) { P.uv[m][0] = (unsigned char)u; P.uv[m][1] = (unsigned char)v; m++; }
+    build_s16_schedule(P);
 }
 
 uint64_t cells_of(int n, int L)
@@ -263,7 +318,7 @@ struct Locus {
 // Runs the full pipeline for `recs` on one device.  If d_raw != nullptr the raw sequences already
 // live on the device (offsets h_off are into that buffer) and no results are downloaded.
 void run_device(Device &D, const char *seqs, const uint64_t *h_off, const std::vector<uint32_t> &recs, int L,
-                const char *d_raw, bool download, cudaStream_t user_stream, Partial &out)
+                const char *d_raw, bool download, cudaStream_t user_stream, bool force_wide, Partial &out)
 {
     out.st = mirfold_stats{};
     out.st.n_devices = 1;
@@ -367,12 +422,15 @@ void run_device(Device &D, const char *seqs, const uint64_t *h_off, const std::v
         CK(D.startlist.ensure(list_acc * 4));
         CK(D.fail.ensure(4));
         CK(cudaMemsetAsync(D.fail.p, 0, 4, st));
+        CK(D.fillflags.ensure((size_t)nl * 4));
+        CK(cudaMemsetAsync(D.fillflags.p, 0, (size_t)nl * 4, st));
         CK(cudaEventRecord(D.ev[1], st));
         // ---- K1..K3
         const LocusDesc *dl = D.loci.as<LocusDesc>();
         CK(launch_prepare(raw_dev, dl, nl, seq_acc, D.codes.as<unsigned char>(), D.F.as<int>(), st));
         CK(cudaEventRecord(D.ev[2], st));
-        FillLaunch fa{dl, nl, max_n, D.codes.as<unsigned char>(), D.C.as<int>(), D.M.as<int>(), D.ring.as<int>(), D.dP, {0, 0, 0, 0, 0}};
+        FillLaunch fa{dl, nl, max_n, D.codes.as<unsigned char>(), D.C.as<int>(), D.M.as<int>(), D.ring.as<int>(), D.dP, {0, 0, 0, 0, 0},
+                      D.fillflags.as<int>(), force_wide ? 1 : 0};
         {   // loci are sorted by descending n: stride buckets are contiguous
             int k = 0;
             const int lim[3] = {608, 352, 160};
@@ -580,6 +638,7 @@ int mirfold_open(mirfold_ctx **pctx, const int *device_ids, int n_devices, const
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&D.stream, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaMalloc(&D.dP, sizeof(DevParams));
         if (e == cudaSuccess) e = cudaMemcpy(D.dP, hp, sizeof(DevParams), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = fill_configure_device();
         for (auto &ev : D.ev) if (e == cudaSuccess) e = cudaEventCreate(&ev);
         size_t fr = 0, tot = 0;
         if (e == cudaSuccess) e = cudaMemGetInfo(&fr, &tot);
@@ -612,8 +671,10 @@ static void add_stats(mirfold_stats &a, const mirfold_stats &b)
 }
 
 static int fold_impl(mirfold_ctx *ctx, const char *seqs, const uint64_t *seq_off, uint32_t nseq, int span_L,
-                     const char *d_raw, bool download, void *stream, mirfold_result **out)
+                     const char *d_raw, bool download, void *stream, uint32_t flags, mirfold_result **out)
 {
+    static const bool env_wide = getenv("MIRFOLD_FORCE_WIDE") != nullptr;   // A/B runs of bench.py
+    const bool force_wide = (flags & MIRFOLD_FLAG_WIDE) != 0 || env_wide;
     if (!ctx || !out || !seq_off || (!seqs && !d_raw && nseq)) return MIRFOLD_ERR_ARG;
     if (span_L < 5 || span_L > MF_MAX_SPAN) { ctx->last_error = "span_L out of range [5, 4096]"; return MIRFOLD_ERR_ARG; }
     *out = nullptr;
@@ -641,11 +702,11 @@ static int fold_impl(mirfold_ctx *ctx, const char *seqs, const uint64_t *seq_off
         std::lock_guard<std::mutex> lk(ctx->pool_mu);
         for (int g = 0; g < G && !ctx->arena_pool.empty(); g++) { parts[g].arena = ctx->arena_pool.back(); ctx->arena_pool.pop_back(); }
     }
-    if (G == 1) run_device(ctx->devs[0], seqs, seq_off, shard[0], span_L, d_raw, download, (cudaStream_t)stream, parts[0]);
+    if (G == 1) run_device(ctx->devs[0], seqs, seq_off, shard[0], span_L, d_raw, download, (cudaStream_t)stream, force_wide, parts[0]);
     else {
         std::vector<std::thread> th;
         for (int g = 0; g < G; g++)
-            th.emplace_back([&, g] { run_device(ctx->devs[g], seqs, seq_off, shard[g], span_L, nullptr, download, nullptr, parts[g]); });
+            th.emplace_back([&, g] { run_device(ctx->devs[g], seqs, seq_off, shard[g], span_L, nullptr, download, nullptr, force_wide, parts[g]); });
         for (auto &t : th) t.join();
     }
     for (int g = 0; g < G; g++)
@@ -717,16 +778,15 @@ static int fold_impl(mirfold_ctx *ctx, const char *seqs, const uint64_t *seq_off
 int mirfold_fold(mirfold_ctx *ctx, const char *seqs, const uint64_t *seq_off, uint32_t nseq, int span_L, uint32_t flags,
                  mirfold_result **out)
 {
-    (void)flags;
-    return fold_impl(ctx, seqs, seq_off, nseq, span_L, nullptr, true, nullptr, out);
+    return fold_impl(ctx, seqs, seq_off, nseq, span_L, nullptr, true, nullptr, flags, out);
 }
 
 int mirfold_fold_device(mirfold_ctx *ctx, const void *d_seqs, const void *d_seq_off, const uint64_t *h_seq_off,
                         uint32_t nseq, int span_L, uint32_t flags, void *stream, mirfold_result **out)
 {
-    (void)flags; (void)d_seq_off;
+    (void)d_seq_off;
     if (!d_seqs) return MIRFOLD_ERR_ARG;
-    return fold_impl(ctx, nullptr, h_seq_off, nseq, span_L, (const char *)d_seqs, false, stream, out);
+    return fold_impl(ctx, nullptr, h_seq_off, nseq, span_L, (const char *)d_seqs, false, stream, flags, out);
 }
 
 void mirfold_free_result(mirfold_result *res)
@@ -741,7 +801,8 @@ void mirfold_free_result(mirfold_result *res)
     delete R;
 }
 
-int mirfold_debug_matrices(mirfold_ctx *ctx, const char *seq, uint32_t n, int span_L, int32_t *c, int32_t *m, int32_t *f3)
+int mirfold_debug_matrices(mirfold_ctx *ctx, const char *seq, uint32_t n, int span_L, uint32_t flags, int32_t *c, int32_t *m,
+                           int32_t *f3)
 {
     if (!ctx || !seq || n < 5 || !c || !m || !f3) return MIRFOLD_ERR_ARG;
     Device &D = ctx->devs[0];
@@ -763,7 +824,10 @@ int mirfold_debug_matrices(mirfold_ctx *ctx, const char *seq, uint32_t n, int sp
     CK(cudaMemcpyAsync(D.loci.p, &d, sizeof d, cudaMemcpyHostToDevice, st));
     const LocusDesc *dl = D.loci.as<LocusDesc>();
     CK(launch_prepare(D.raw.as<char>(), dl, 1, n + 3, D.codes.as<unsigned char>(), D.F.as<int>(), st));
-    FillLaunch fa{dl, 1, (int)n, D.codes.as<unsigned char>(), D.C.as<int>(), D.M.as<int>(), D.ring.as<int>(), D.dP, {0, 0, 0, 0, 1}};
+    CK(D.fillflags.ensure(4));
+    CK(cudaMemsetAsync(D.fillflags.p, 0, 4, st));
+    FillLaunch fa{dl, 1, (int)n, D.codes.as<unsigned char>(), D.C.as<int>(), D.M.as<int>(), D.ring.as<int>(), D.dP, {0, 0, 0, 0, 1},
+                  D.fillflags.as<int>(), (flags & MIRFOLD_FLAG_WIDE) ? 1 : 0};
     fa.bucket_first[1] = d.n > 608 ? 1 : 0;
     fa.bucket_first[2] = d.n > 352 ? 1 : 0;
     fa.bucket_first[3] = d.n > 160 ? 1 : 0;

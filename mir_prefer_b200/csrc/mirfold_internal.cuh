@@ -19,6 +19,23 @@
 #define MF_SKEW_A 11    /* ring row rotation per diagonal: bank class of (u,v) = (u - 11*(u+v)) mod 32 */
 #define MF_MAX_SPAN 4096 /* hairpin-size table length; PRECURSOR_LEN is capped at 3000 (MP:168) */
 
+/* ---- 16-bit pair ring of the narrow fill kernel (k_fill_s16) ------------------------------------
+ * Two adjacent diagonals share one 32-bit shared-memory word per row (lo = even diagonal), so one LDS
+ * + one VIADDMNMX.S16x2 evaluates two interior-loop terms.  Values are exact as long as every c of the
+ * locus stays above MF16_GUARD; a locus that violates it is flagged and redone by the 32-bit kernel. */
+#define MF16_NPS 17        /* pair slots: 16 read + 1 written per diagonal                         */
+#define MF16_NQG 8         /* generic word-terms per lane                                           */
+#define MF16_NQB 2         /* bulge word-terms per lane                                             */
+#define MF16_NQ (MF16_NQG + MF16_NQB)
+#define MF16_NMG 2         /* leading generic iterations that carry a half-word mask                */
+#define MF16_NMK (MF16_NMG + MF16_NQB)
+#define MF16_SKEW 17       /* row rotation per pair slot: bank class of a word-term = (x - 17 m) mod 32 */
+#define MF16_INF 31000
+#define MF16_INF2 0x79187918u
+#define MF16_VALID 20000   /* anything >= this after the min is "no loop"                           */
+#define MF16_GUARD (-32000)
+#define MF16_DBIAS 128
+
 struct DevParams {
     int hairpinE[MF_MAX_SPAN + 2];  // by loop size, incl. the lxc*log extrapolation (A.2)
     int bulge[31], internal_loop[31];
@@ -30,6 +47,11 @@ struct DevParams {
     int ilc[16][32];               // generic kernel: interior-loop constants per (iteration, lane); INF = masked
     int gen_c[MF_GEN_ITERS][32];   // smem kernel: constant of the term lane l evaluates in iteration k (INF = none)
     int gen_us[MF_GEN_ITERS][32];  //              its u | (u+v) << 8 | valid << 16
+    // narrow kernel, per parity of d: word-term descriptors m | xoff << 4 | ring << 10 | null << 11,
+    // packed 16-bit constants (lo | hi << 16) and half-word keep masks of the masked iterations
+    unsigned int s16_td[2][MF16_NQ][32];
+    unsigned int s16_cst[2][MF16_NQ][32];
+    unsigned int s16_mk[2][MF16_NMK][32];
     int MLclosing, TerminalAU;
     short tetra[4096];             // tetraloop bonus by 2-bit packed 6-mer
     unsigned char pair[64];        // BP_pair[S_i*8+S_j]
@@ -78,10 +100,13 @@ struct FillLaunch {
     int *C, *M, *ring;
     const DevParams *P;
     int bucket_first[5];  // loci sorted by descending n: [generic | <=608 | <=352 | <=160 | end)
+    int *flags;           // per locus: 1 = the 16-bit kernel left its range, redo with the 32-bit kernel
+    int force_wide;       // skip the 16-bit kernel (MIRFOLD_FLAG_WIDE)
 };
 cudaError_t launch_prepare(const char *raw, const LocusDesc *loci, int nloci, unsigned long long total_codes,
                            unsigned char *codes, int *F, cudaStream_t st);
 cudaError_t launch_fill(const FillLaunch &a, cudaStream_t st);
+cudaError_t fill_configure_device();
 cudaError_t launch_f3(const LocusDesc *loci, int nloci, const unsigned char *codes, const int *C, int *F,
                       const DevParams *P, cudaStream_t st);
 

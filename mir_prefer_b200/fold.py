@@ -20,6 +20,7 @@ from . import _lib
 from ._lib import MirfoldError
 
 DEFAULT_PARAMSET = b"vienna-1.8.5-d1"
+FLAG_WIDE = 1   # MIRFOLD_FLAG_WIDE: force the 32-bit fill kernel (results are identical)
 HIT_DTYPE = np.dtype([("start", "<i4"), ("len", "<i4"), ("mfe_dcal", "<i4"), ("reserved", "<i4"), ("ss_off", "<u8")])
 
 
@@ -151,28 +152,28 @@ class MirFold:
         buf = np.frombuffer(b"".join(bs), np.uint8) if bs else np.zeros(0, np.uint8)
         return buf, off
 
-    def fold_packed(self, buf, off, span):
+    def fold_packed(self, buf, off, span, flags=0):
         """buf: uint8 array of concatenated raw sequence tokens, off: uint64[nseq+1]."""
         buf = np.ascontiguousarray(buf, np.uint8)
         off = np.ascontiguousarray(off, np.uint64)
         nseq = len(off) - 1
         res = C.POINTER(_lib.Result)()
         rc = self._lib.mirfold_fold(self._ctx, buf.ctypes.data_as(C.c_void_p), off.ctypes.data_as(C.POINTER(C.c_uint64)),
-                                    nseq, int(span), 0, C.byref(res))
+                                    nseq, int(span), int(flags), C.byref(res))
         if rc != 0:
             self._raise(rc)
         return FoldResult(self._lib, res, nseq)
 
-    def fold(self, seqs, span):
+    def fold(self, seqs, span, flags=0):
         buf, off = self.pack(seqs)
-        return self.fold_packed(buf, off, span)
+        return self.fold_packed(buf, off, span, flags)
 
-    def fold_device(self, d_ptr, off, span, stream=None):
+    def fold_device(self, d_ptr, off, span, stream=None, flags=0):
         """Kernel-only path: raw sequences already in HBM at d_ptr (int), results stay on device."""
         off = np.ascontiguousarray(off, np.uint64)
         res = C.POINTER(_lib.Result)()
         rc = self._lib.mirfold_fold_device(self._ctx, C.c_void_p(d_ptr), None, off.ctypes.data_as(C.POINTER(C.c_uint64)),
-                                           len(off) - 1, int(span), 0, C.c_void_p(stream or 0), C.byref(res))
+                                           len(off) - 1, int(span), int(flags), C.c_void_p(stream or 0), C.byref(res))
         if rc != 0:
             self._raise(rc)
         return FoldResult(self._lib, res, len(off) - 1)
@@ -185,7 +186,7 @@ class MirFold:
             self._raise(rc)
         return a.value, b.value
 
-    def debug_matrices(self, seq, span):
+    def debug_matrices(self, seq, span, flags=0):
         """(c, fML, f3) of one sequence in the oracle's [i][d] layout (tests only)."""
         b = seq.encode() if isinstance(seq, str) else seq
         n = len(b)
@@ -193,7 +194,7 @@ class MirFold:
         c = np.empty((n + 2, W), np.int32)
         m = np.empty((n + 2, W), np.int32)
         f3 = np.empty(n + 4, np.int32)
-        rc = self._lib.mirfold_debug_matrices(self._ctx, b, n, int(span), c.ctypes.data_as(C.c_void_p),
+        rc = self._lib.mirfold_debug_matrices(self._ctx, b, n, int(span), int(flags), c.ctypes.data_as(C.c_void_p),
                                               m.ctypes.data_as(C.c_void_p), f3.ctypes.data_as(C.c_void_p))
         if rc != 0:
             self._raise(rc)

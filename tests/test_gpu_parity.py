@@ -51,6 +51,37 @@ def test_matrices_cell_for_cell(mf, oracle):
         assert (o["f3"][:n + 3] == f3[:n + 3]).all()
 
 
+def test_wide_kernel_flag_gives_identical_results(mf, oracle):
+    """MIRFOLD_FLAG_WIDE forces the 32-bit fill kernel for every locus; both kernels are bit-exact."""
+    from mir_prefer_b200.fold import FLAG_WIDE
+    seqs = synth_loci(21, 48, "parity") + synth_loci(22, 24, (20, 200)) + synth_loci(23, 8, (610, 900))
+    with mf.fold(seqs, 300) as a, mf.fold(seqs, 300, flags=FLAG_WIDE) as b:
+        for r, s in enumerate(seqs):
+            assert a.hits(r) == b.hits(r) and a.total(r) == b.total(r)
+            if r % 8 == 0:
+                o = oracle.fold(s, 300)
+                assert a.hits(r) == o["hits"] and a.total(r) == o["total"]
+    s = synth_loci(6, 1, (320, 320))[0]
+    for fl in (0, FLAG_WIDE):
+        o = oracle.fold(s, 300, matrices=True)
+        c, m, f3 = mf.debug_matrices(s, 300, flags=fl)
+        assert (o["c"] == c).all() and (np.minimum(o["m"], 1000000) == np.minimum(m, 1000000)).all()
+        assert (o["f3"][:len(s) + 3] == f3[:len(s) + 3]).all()
+
+
+def test_energies_below_16bit_range_fall_back_to_wide_kernel(mf, oracle):
+    """Windows below -320 kcal/mol (perfect GC helices) leave the 16-bit ring's range: the locus is
+    flagged on the device and redone by the 32-bit kernel, transparently."""
+    seqs = ["GC" * 150, "G" * 148 + "AAAA" + "C" * 148, "GC" * 100 + "A" * 7 + "GC" * 100,
+            "G" * 100 + "UUCG" + "C" * 100, "GGGGCCCC" * 60, synth_loci(5, 1, (300, 300))[0]]
+    for L in (300, 150):
+        assert_same(mf, oracle, seqs, L)
+    o = oracle.fold(seqs[0], 300, matrices=True)
+    assert o["c"].min() < -32000          # the case really is out of range
+    c, m, f3 = mf.debug_matrices(seqs[0], 300)
+    assert (o["c"] == c).all() and (np.minimum(o["m"], 1000000) == np.minimum(m, 1000000)).all()
+
+
 def test_edge_lengths_and_empty(mf, oracle):
     seqs = ["", "A", "ACG", "ACGU", "GCGCA", "GGGAAACCC", "GGGGAAAACCCC", "A" * 21, "ACGUNNNACGU", "N" * 50,
             "GGGGGTTTTCCCCCAAAAGGGGGTTTTCCCCC"]
