@@ -167,11 +167,13 @@ __device__ __forceinline__ int dev_fml(const DevParams *__restrict__ P, const un
     return min(m, rD[(d & (MF_RING_DML - 1)) * NS + i - 1]);
 }
 
+__device__ __forceinline__ void dev_prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 // phase A: DML for the strip d..d1 from fML diagonals <= d-1.  One (row, part) per thread; `part`
 // splits the e-range when the strip has fewer rows than the CTA has threads.
 template <int NT, class StrideT>
 __device__ __forceinline__ void dev_phase_a(const int *Mb, int *rD, StrideT NS, int n, int d,
-                                            int d1, int tid)
+                                            int d1, int tid, bool prefetch = true)
 {
     const int emax = d1 - 5;  // e ranges 4..emax for the widest diagonal of the strip
     if (emax < 4) return;
@@ -194,6 +196,13 @@ __device__ __forceinline__ void dev_phase_a(const int *Mb, int *rD, StrideT NS, 
         const int emain = min(e1, d - 5);                   // all five diagonals accept e <= d-5
         int e = e0;
         for (; e + 3 <= emain; e += 4) {
+            if (prefetch && e + 11 <= emain) {   // pull the two new cache lines of each step two batches ahead into L1
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    dev_prefetch_l1(pa + (8 + k) * NS);
+                    dev_prefetch_l1(pb - (8 + k) * (NS - 1));
+                }
+            }
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 const int av = pa[k * NS];
@@ -227,6 +236,86 @@ __device__ __forceinline__ void dev_phase_a(const int *Mb, int *rD, StrideT NS, 
                 if (nparts == 1) *dst = acc[s];
                 else atomicMin(dst, acc[s]);
             }
+    }
+}
+
+
+// phase A on 16-bit row pairs (narrow kernel): Mp[diag][x] holds fML16 of rows x+1 (lo) and x+2 (hi),
+// so a thread owns two rows and one LDG + one VIADDMNMX.S16x2 covers two split terms.  Values are
+// exact while every finite fML of the locus stays above MF16M_GUARD (fML16 INF = 16383: INF+INF and
+// INF+finite stay above MF16M_VALID and never wrap); otherwise the locus is flagged for the 32-bit kernel.
+template <int NT, class StrideT>
+__device__ __forceinline__ void dev_phase_a16(const unsigned int *Mp, int *rD, StrideT NS, int n, int d, int d1,
+                                              int tid, bool prefetch)
+{
+    const int emax = d1 - 5;  // e ranges 4..emax for the widest diagonal of the strip
+    if (emax < 4) return;
+    const int R = n - d, RP = (R + 1) >> 1;
+    const int Rpad = (RP + 31) & ~31;
+    int nparts = NT / Rpad;
+    nparts = max(1, min(nparts, 8));
+    const int span = emax - 3;
+    const int per = (span + nparts - 1) / nparts;
+    for (int base = 0; base < Rpad * nparts; base += NT) {
+        const int idx = base + tid;
+        const int part = idx / Rpad, i = 2 * (idx - part * Rpad) + 1;   // rows i (lo half) and i+1 (hi half)
+        if (part >= nparts || i > R) continue;
+        const int e0 = 4 + part * per, e1 = min(emax, e0 + per - 1);
+        if (e0 > e1) continue;
+        const int ns = min(d1 - d, n - d - i) + 1;                  // valid strip diagonals for row i
+        const int nsh = min(d1 - d, n - d - i - 1) + 1;             // ... and for row i+1 (0 if it has no cell on diagonal d)
+        const unsigned int *pa = Mp + (e0 - 4) * NS + (i - 1);       // fML(i, i+e) | fML(i+1, i+1+e)
+        const unsigned int *pb = Mp + (d - 5 - e0) * NS + (i + e0);  // fML(i+e+1, i+d) | fML(i+e+2, i+1+d)   (+ s*NS for d+s)
+        unsigned int acc[5] = {MF16M_INF2, MF16M_INF2, MF16M_INF2, MF16M_INF2, MF16M_INF2};
+        const int emain = min(e1, d - 5);
+        int e = e0;
+        for (; e + 3 <= emain; e += 4) {
+            if (prefetch && e + 11 <= emain) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    dev_prefetch_l1(pa + (8 + k) * NS);
+                    dev_prefetch_l1(pb - (8 + k) * (NS - 1));
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const unsigned int av = pa[k * NS];
+#pragma unroll
+                for (int s = 0; s < 5; s++)
+                    if (s < ns) acc[s] = __viaddmin_s16x2(av, pb[s * NS - k * (NS - 1)], acc[s]);
+            }
+            pa += 4 * NS;
+            pb -= 4 * (NS - 1);
+        }
+        for (; e <= emain; e++) {
+            const unsigned int av = pa[0];
+#pragma unroll
+            for (int s = 0; s < 5; s++)
+                if (s < ns) acc[s] = __viaddmin_s16x2(av, pb[s * NS], acc[s]);
+            pa += NS;
+            pb -= (NS - 1);
+        }
+        for (; e <= e1; e++) {   // tail: diagonal d+s accepts e <= d+s-5
+            const unsigned int av = pa[0];
+#pragma unroll
+            for (int s = 1; s < 5; s++)
+                if (s < ns && e <= d + s - 5) acc[s] = __viaddmin_s16x2(av, pb[s * NS], acc[s]);
+            pa += NS;
+            pb -= (NS - 1);
+        }
+#pragma unroll
+        for (int s = 0; s < 5; s++) {
+            const int lo = (int)(short)(acc[s] & 0xffffu), hi = (int)acc[s] >> 16;
+            int *dst = &rD[((d + s) & (MF_RING_DML - 1)) * NS + (i - 1)];
+            if (s < ns && lo < MF16M_VALID) {
+                if (nparts == 1) dst[0] = lo;
+                else atomicMin(dst, lo);
+            }
+            if (s < nsh && hi < MF16M_VALID) {
+                if (nparts == 1) dst[1] = hi;
+                else atomicMin(dst + 1, hi);
+            }
+        }
     }
 }
 
@@ -306,7 +395,7 @@ __global__ void __launch_bounds__(NT, MINB) k_fill_smem(FillLaunch a)
     // the next iteration and later DML strips read) and build the typed list of diagonal it+1.
     for (int it = 4; it <= dmax + 1; it++) {
         if (it >= 5 && (it - 5) % 5 == 0 && it - 1 <= dmax) {
-            dev_phase_a<NT>(Mb, rD, NS, n, it - 1, min(it + 3, dmax), tid);   // DML strip [it-1, it+3]
+            dev_phase_a<NT>(Mb, rD, NS, n, it - 1, min(it + 3, dmax), tid, !(a.opts & 1));   // DML strip [it-1, it+3]
             __syncthreads();
         }
         if (wid < NWC) {
@@ -414,17 +503,28 @@ __device__ __forceinline__ unsigned dev_lds(unsigned addr)
     return w;
 }
 
+#ifndef MF16_NWM
+#define MF16_NWM(NT) (((NT) / 32 * 3 + 4) / 8)   /* fML/list warps of the narrow kernel: 6 of 16, 5 of 12, 3 of 8 */
+#endif
 template <int NS>
 struct Fill16Smem {
     static constexpr int RS = NS + 32;
     static constexpr int ring_words = (MF16_NPS + 1) * RS;   // + one all-INF row
-    static constexpr size_t bytes = (size_t)2 * ring_words * 4 + (size_t)2 * NS * 4 + 200 * 4 + 32 * 4 + 2 * (NS + 8) + 64 + 16;
+    static constexpr int sched_words = 2 * MF16_NQ * 32 * 2 + 2 * MF16_NMK * 32;   // sOff, sCst (both parities), sMk
+    static constexpr size_t bytes = (size_t)2 * ring_words * 4 + (size_t)5 * NS * 4 + 200 * 4 + (size_t)sched_words * 4 +
+                                    2 * (NS + 8) + 64 + 16;
 };
 
-__device__ __forceinline__ int dev_row16(int d, int m, int RS)
-{   // word offset of pair slot m (relative to diagonal d) inside a ring
-    const int pp = ((d - 2) >> 1) - m;
-    return pp < 0 ? MF16_NPS * RS : (pp % MF16_NPS) * RS + ((MF16_SKEW * pp) & 31);
+// Byte offset (from the start of sG) of the word-term `td` of lane `lane` for a cell on diagonal d.
+// A lane without a term in this iteration reads the all-INF row at the bank its own class would use,
+// which no other lane touches in the same instruction.
+__device__ __forceinline__ unsigned dev_term_off16(unsigned td, int lane, int d, int RS, int RW)
+{
+    const int ppb = (d - 2) >> 1;
+    if (td >> 11) return (unsigned)(MF16_NPS * RS + ((lane + MF16_SKEW * ppb) & 31)) * 4u;
+    const int m = td & 15, xo = (td >> 4) & 63, pp = ppb - m;
+    const int row = pp < 0 ? MF16_NPS * RS : (pp % MF16_NPS) * RS + ((MF16_SKEW * pp) & 31);   // pp < 0: all-INF row (d < 34 only)
+    return (unsigned)(((td >> 10) & 1) * RW + row + xo) * 4u;
 }
 __device__ __forceinline__ void dev_ring16_put(unsigned int *ring, int RS, int d, int x, int v)
 {
@@ -433,19 +533,106 @@ __device__ __forceinline__ void dev_ring16_put(unsigned int *ring, int RS, int d
     w[d & 1] = (unsigned short)v;
 }
 
-template <int NS, int NT, int MINB>
+
+// 16-bit ring read: value of diagonal dd at row index x (= p-1)
+__device__ __forceinline__ int dev_ring16_get(const unsigned int *ring, int RS, int dd, int x)
+{
+    const int pp = dd >> 1;
+    const short *w = (const short *)(ring + (pp % MF16_NPS) * RS + ((MF16_SKEW * pp) & 31) + x);
+    return w[dd & 1];
+}
+__device__ __forceinline__ int dev_rtype(int t) { return t ? (((t - 1) ^ 1) + 1) : 0; }   // {0,2,1,4,3,6,5}
+
+// The seven table-driven two-loops + hairpin + d1 multiloop closing of a typed cell, narrow kernel:
+// branch-free (all lookups of the seven loops are independent and overlap) and with c(p,q) read from
+// the shared-memory bulge ring (c + AU) instead of the band.
+template <class StrideT>
+__device__ __forceinline__ int dev_cell_tail16(const DevParams *__restrict__ P, const unsigned char *sS,
+                                               const unsigned char *sS1, const unsigned char *sPair,
+                                               const unsigned int *sB, int RS, const int *rD, StrideT NS, int i,
+                                               int d, int t, int si1, int sj1, int K)
+{
+    const int j = i + d;
+    const int AUp = P->TerminalAU;
+    int best = MF_INF;
+#pragma unroll
+    for (int m = 0; m < 7; m++) {
+        const int u = (m == 1 || m == 3 || m == 4) ? 1 : (m >= 5 ? 2 : 0);
+        const int v = (m == 2 || m == 3 || m == 5) ? 1 : ((m == 4 || m == 6) ? 2 : 0);
+        // m: 0 (0,0)  1 (1,0)  2 (0,1)  3 (1,1)  4 (1,2)  5 (2,1)  6 (2,2)
+        const bool ok = (u + v <= K);
+        const int p = ok ? i + 1 + u : i + 1, q = ok ? j - 1 - v : j - 1;   // clamped: always a legal address
+        const int t2 = sPair[sS[p] * 8 + sS[q]];
+        const int r2 = dev_rtype(t2);
+        const int c2 = dev_ring16_get(sB, RS, ok ? d - 2 - u - v : d - 2, p - 1) - (t2 > 2 ? AUp : 0);
+        const int sp1 = sS1[p - 1], sq1 = sS1[q + 1];
+        int e;
+        if (m == 0) e = P->stack[t * 8 + r2];
+        else if (m == 1 || m == 2) e = P->bulge[1] + P->stack[t * 8 + r2];
+        else if (m == 3) e = P->int11[((t * 8 + r2) * 5 + si1) * 5 + sj1];
+        else if (m == 4) e = P->int21[(((t * 8 + r2) * 5 + si1) * 5 + sq1) * 5 + sj1];           // n1 = 1, n2 = 2
+        else if (m == 5) e = P->int21[(((r2 * 8 + t) * 5 + sq1) * 5 + si1) * 5 + sp1];           // n1 = 2, n2 = 1
+        else e = P->int22[((((t * 8 + r2) * 5 + si1) * 5 + sp1) * 5 + sq1) * 5 + sj1];
+        if (ok && t2) best = min(best, e + c2);
+    }
+    best = min(best, dev_hairpin(P, sS, sS1, i, j, t));
+    const int tt = dev_rtype(t);
+    const int d3 = P->dangle3[tt * 5 + si1], d5 = P->dangle5[tt * 5 + sj1];
+    int dec = MF_INF;
+    if (d - 2 >= 4) dec = rD[((d - 2) & (MF_RING_DML - 1)) * NS + i];                          // DML(i+1,j-1)
+    if (d - 3 >= 4) {
+        dec = min(dec, rD[((d - 3) & (MF_RING_DML - 1)) * NS + i + 1] + d3);                   // DML(i+2,j-1)
+        dec = min(dec, rD[((d - 3) & (MF_RING_DML - 1)) * NS + i] + d5);                       // DML(i+1,j-2)
+    }
+    if (d - 4 >= 4) dec = min(dec, rD[((d - 4) & (MF_RING_DML - 1)) * NS + i + 1] + d3 + d5);  // DML(i+2,j-2)
+    return min(best, P->MLclosing + P->MLintern[t] + dec);
+}
+
+// fML(i,j) for the narrow kernel: c of the three newest diagonals comes from the shared-memory bulge
+// ring (c + AU, exact inside the guarded range) and fML of diagonal d-1 from a shared row buffer, so
+// the only global read is DML(i,j).
+template <class StrideT>
+__device__ __forceinline__ int dev_fml16(const DevParams *__restrict__ P, const unsigned char *sS, const unsigned char *sS1,
+                                         const unsigned char *sPair, const unsigned int *sB, int RS, const int *Mprev,
+                                         const int *rD, StrideT NS, int i, int d, int Ls)
+{
+    const int j = i + d;
+    const int AUp = P->TerminalAU;
+    const int t = (d < Ls) ? sPair[sS[i] * 8 + sS[j]] : 0;
+    int m = MF_INF;
+    if (d - 1 >= 4) {
+        m = min(Mprev[i], Mprev[i - 1]);                            // fML(i+1,j), fML(i,j-1)
+        const int ta = sPair[sS[i + 1] * 8 + sS[j]];                // (i+1, j)
+        if (ta) m = min(m, dev_ring16_get(sB, RS, d - 1, i) - (ta > 2 ? AUp : 0) + P->dangle5[ta * 5 + sS1[i]] + P->MLintern[ta]);
+        const int tb = sPair[sS[i] * 8 + sS[j - 1]];                // (i, j-1)
+        if (tb) m = min(m, dev_ring16_get(sB, RS, d - 1, i - 1) - (tb > 2 ? AUp : 0) + P->dangle3[tb * 5 + sS1[j]] + P->MLintern[tb]);
+    }
+    if (t) m = min(m, dev_ring16_get(sB, RS, d, i - 1) - (t > 2 ? AUp : 0) + P->MLintern[t]);
+    if (d - 2 >= 4) {
+        const int tc = sPair[sS[i + 1] * 8 + sS[j - 1]];            // (i+1, j-1)
+        if (tc) m = min(m, dev_ring16_get(sB, RS, d - 2, i) - (tc > 2 ? AUp : 0) + P->dangle5[tc * 5 + sS1[i]] +
+                               P->dangle3[tc * 5 + sS1[j]] + P->MLintern[tc]);
+    }
+    return min(m, rD[(d & (MF_RING_DML - 1)) * NS + i - 1]);
+}
+
+template <int NS, int NT, int NWM, int MINB>
 __global__ void __launch_bounds__(NT, MINB) k_fill_s16(FillLaunch a)
 {
     constexpr int RS = Fill16Smem<NS>::RS, RW = Fill16Smem<NS>::ring_words;
-    constexpr int NW = NT / 32, NWM = NW / 4, NWC = NW - NWM;
+    constexpr int NW = NT / 32, NWC = NW - NWM;
     constexpr int CT = NWC * 32, MT = NWM * 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned int *sG = (unsigned int *)smem_raw;              // [18][RS]
     unsigned int *sB = sG + RW;                               // [18][RS]
     unsigned int *sList = sB + RW;                            // [2][NS]  i*4 | (AU - mismatchI + bias) << 16
-    int *sMM = (int *)(sList + 2 * NS);                       // mismatchI[200]
-    int *sRow = sMM + 200;                                    // [2][16] pair-slot row offsets of diagonal d (by parity)
-    unsigned char *sS = (unsigned char *)(sRow + 32);         // [NS+8]
+    int *sMy = (int *)(sList + 2 * NS);                       // [NS] interior-loop minimum of the listed cell
+    int *sMrow = sMy + NS;                                    // [2][NS] fML of the last two diagonals (by parity)
+    int *sMM = sMrow + 2 * NS;                                // mismatchI[200]
+    unsigned int *sOff = (unsigned int *)(sMM + 200);         // [2][NQ][32] word-term byte offsets of diagonal d (by parity of d)
+    unsigned int *sCst = sOff + 2 * MF16_NQ * 32;             // [2][NQ][32] packed constants (by parity)
+    unsigned int *sMk = sCst + 2 * MF16_NQ * 32;              // [2][NMK][32] half-word keep masks (by parity)
+    unsigned char *sS = (unsigned char *)(sMk + 2 * MF16_NMK * 32);   // [NS+8]
     unsigned char *sS1 = sS + NS + 8;
     unsigned char *sPair = sS1 + NS + 8;                      // [64]
     __shared__ int sCount[3];
@@ -467,10 +654,13 @@ __global__ void __launch_bounds__(NT, MINB) k_fill_s16(FillLaunch a)
     if (tid < 64) sPair[tid] = P->pair[tid];
     if (tid < 3) sCount[tid] = 0;
     if (tid == 0) sFlag = 0;
-    if (tid < 16) sRow[tid] = dev_row16(4, tid, RS);
+    for (int k = tid; k < 2 * MF16_NQ * 32; k += NT) sCst[k] = (&P->s16_cst[0][0][0])[k];
+    for (int k = tid; k < 2 * MF16_NMK * 32; k += NT) sMk[k] = (&P->s16_mk[0][0][0])[k];
+    for (int k = tid; k < MF16_NQ * 32; k += NT) sOff[k] = dev_term_off16((&P->s16_td[0][0][0])[k], k & 31, 4, RS, RW);
 
     int *Cb = a.C + L.band_off;
     int *Mb = a.M + L.band_off;
+    unsigned int *Mp = a.Mp + L.band_off;
     int *rD = a.ring + L.ring_off;   // [MF_RING_DML][NS]
     for (int k = tid; k < MF_RING_DML * NS; k += NT) rD[k] = MF_INF;
     __syncthreads();
@@ -491,7 +681,9 @@ __global__ void __launch_bounds__(NT, MINB) k_fill_s16(FillLaunch a)
 
     for (int it = 4; it <= dmax + 1; it++) {
         if (it >= 5 && (it - 5) % 5 == 0 && it - 1 <= dmax) {
-            dev_phase_a<NT>(Mb, rD, NS, n, it - 1, min(it + 3, dmax), tid);   // DML strip [it-1, it+3]
+            // DML strip [it-1, it+3]
+            if (a.opts & 2) dev_phase_a<NT>(Mb, rD, NS, n, it - 1, min(it + 3, dmax), tid, !(a.opts & 1));
+            else dev_phase_a16<NT>(Mp, rD, NS, n, it - 1, min(it + 3, dmax), tid, !(a.opts & 1));
             __syncthreads();
         }
         if (wid < NWC) {
@@ -505,64 +697,72 @@ __global__ void __launch_bounds__(NT, MINB) k_fill_s16(FillLaunch a)
                 unsigned off[MF16_NQ], cst[MF16_NQ], mk[MF16_NMK];
 #pragma unroll
                 for (int q = 0; q < MF16_NQ; q++) {
-                    const unsigned td = P->s16_td[par][q][lane];
-                    const int m = td & 15, xo = (td >> 4) & 63;
-                    const int row = (td >> 11) ? MF16_NPS * RS : sRow[par * 16 + m];
-                    off[q] = smem_base + (unsigned)(((td >> 10) & 1) * RW + row + xo) * 4u;
+                    off[q] = smem_base + sOff[(par * MF16_NQ + q) * 32 + lane];
                     asm("" : "+r"(off[q]));   // keep the byte address as one register (no re-association in the cell loop)
-                    cst[q] = P->s16_cst[par][q][lane];
+                    cst[q] = sCst[(par * MF16_NQ + q) * 32 + lane];
                 }
 #pragma unroll
-                for (int q = 0; q < MF16_NMK; q++) mk[q] = P->s16_mk[par][q][lane];
+                for (int q = 0; q < MF16_NMK; q++) mk[q] = sMk[(par * MF16_NMK + q) * 32 + lane];
 
+                // phase 1: one typed cell per warp pass -> interior-loop minimum in sMy
                 const int per = (ntyped + NWC - 1) / NWC;
                 const int cend = min(ntyped, wid * per + per);
-                for (int c0 = wid * per; c0 < cend; c0 += 32) {
-                    const int cnt = min(32, cend - c0);
-                    int my = MF16_INF;
-                    for (int k = 0; k < cnt; k++) {
-                        const unsigned e = list[c0 + k];
-                        const unsigned i4 = e & 0xffffu;
-                        unsigned accG = MF16_INF2, accB = MF16_INF2;
+                for (int c = wid * per; c < cend; c++) {
+                    const unsigned e = list[c];
+                    const unsigned i4 = e & 0xffffu;
+                    unsigned accG = MF16_INF2, accB = MF16_INF2;
 #pragma unroll
-                        for (int q = 0; q < MF16_NQG; q++) {
-                            unsigned w = dev_lds(off[q] + i4);
-                            if (q < MF16_NMG) w = (w & mk[q]) | (~mk[q] & MF16_INF2);
-                            accG = __viaddmin_s16x2(w, cst[q], accG);
-                        }
+                    for (int q = 0; q < MF16_NQG; q++) {
+                        unsigned w = dev_lds(off[q] + i4);
+                        if (q < MF16_NMG) w = (w & mk[q]) | (~mk[q] & MF16_INF2);
+                        accG = __viaddmin_s16x2(w, cst[q], accG);
+                    }
 #pragma unroll
-                        for (int q = 0; q < MF16_NQB; q++) {
-                            unsigned w = dev_lds(off[MF16_NQG + q] + i4);
-                            w = (w & mk[MF16_NMG + q]) | (~mk[MF16_NMG + q] & MF16_INF2);
-                            accB = __viaddmin_s16x2(w, cst[MF16_NQG + q], accB);
-                        }
-                        const unsigned dl2 = __byte_perm(e, 0, 0x3232);              // (dl, dl)
-                        const unsigned acc = __viaddmin_s16x2(accB, dl2, accG);      // relative to the outer mismatch
-                        int v = min((int)(short)(acc & 0xffffu), (int)acc >> 16);
-                        v = warp_min(v);
-                        if (lane == k) my = v;
+                    for (int q = 0; q < MF16_NQB; q++) {
+                        unsigned w = dev_lds(off[MF16_NQG + q] + i4);
+                        w = (w & mk[MF16_NMG + q]) | (~mk[MF16_NMG + q] & MF16_INF2);
+                        accB = __viaddmin_s16x2(w, cst[MF16_NQG + q], accB);
                     }
-                    if (lane < cnt) {
-                        const int i = (int)(list[c0 + lane] & 0xffffu) >> 2, j = i + d;
-                        const int t = sPair[sS[i] * 8 + sS[j]];
-                        const int si1 = sS1[i + 1], sj1 = sS1[j - 1];
-                        int best = (my < MF16_VALID) ? my + sMM[(t * 5 + si1) * 5 + sj1] : MF_INF;
-                        best = min(best, dev_cell_tail(P, sS, sS1, sPair, Cb, rD, NS, i, d, t, si1, sj1, K));
-                        const int tt = P->rtype[t];
-                        const int mm = sMM[(tt * 5 + sS1[j + 1]) * 5 + sS1[i - 1]];
-                        Cb[(d - 4) * NS + i - 1] = best;
-                        if (best < MF16_GUARD) sFlag = 1;
-                        dev_ring16_put(sG, RS, d, i - 1, max(best + mm, -32768));
-                        dev_ring16_put(sB, RS, d, i - 1, max(best + (tt > 2 ? AUp : 0), -32768));
-                    }
+                    const unsigned dl2 = __byte_perm(e, 0, 0x3232);              // (dl, dl)
+                    const unsigned acc = __viaddmin_s16x2(accB, dl2, accG);      // relative to the outer mismatch
+                    int v = min((int)(short)(acc & 0xffffu), (int)acc >> 16);
+                    v = warp_min(v);
+                    if (lane == 0) sMy[c] = v;
                 }
-            }
+                asm volatile("bar.sync 1, %0;" ::"n"(CT) : "memory");   // c warps only
+                // phase 2: one typed cell per thread -- small loops, hairpin, multiloop closing, stores
+                for (int c = tid; c < ntyped; c += CT) {
+                    const int i = (int)(list[c] & 0xffffu) >> 2, j = i + d;
+                    const int my = sMy[c];
+                    const int t = sPair[sS[i] * 8 + sS[j]];
+                    const int si1 = sS1[i + 1], sj1 = sS1[j - 1];
+                    int best = (my < MF16_VALID) ? my + sMM[(t * 5 + si1) * 5 + sj1] : MF_INF;
+                    best = min(best, dev_cell_tail16(P, sS, sS1, sPair, sB, RS, rD, NS, i, d, t, si1, sj1, K));
+                    const int tt = dev_rtype(t);
+                    const int mm = sMM[(tt * 5 + sS1[j + 1]) * 5 + sS1[i - 1]];
+                    Cb[(d - 4) * NS + i - 1] = best;
+                    if (best < MF16_GUARD) sFlag = 1;
+                    dev_ring16_put(sG, RS, d, i - 1, max(best + mm, -32768));
+                    dev_ring16_put(sB, RS, d, i - 1, max(best + (tt > 2 ? AUp : 0), -32768));
+                }
+            } else asm volatile("bar.sync 1, %0;" ::"n"(CT) : "memory");
         } else {
             const int mt = tid - CT;
             const int dm = it - 1;
             if (dm >= 4) {
-                for (int i = mt + 1; i <= n - dm; i += MT)
-                    Mb[(dm - 4) * NS + i - 1] = dev_fml(P, sS, sS1, sPair, Cb, Mb, rD, NS, i, dm, Ls);
+                const int *Mprev = sMrow + ((dm - 1) & 1) * NS;
+                int *Mcur = sMrow + (dm & 1) * NS;
+                for (int i = mt + 1; i <= n - dm; i += MT) {
+                    const int m = dev_fml16(P, sS, sS1, sPair, sB, RS, Mprev, rD, NS, i, dm, Ls);
+                    Mb[(dm - 4) * NS + i - 1] = m;
+                    Mcur[i - 1] = m;
+                    // 16-bit copy for the DML strips: lo half of word i-1, hi half of word i-2
+                    const int m16 = (m >= MF_INF / 2) ? MF16M_INF : max(m, -32768);
+                    if (m < MF16M_GUARD) sFlag = 1;
+                    unsigned short *w = (unsigned short *)(Mp + (dm - 4) * NS + i - 1);
+                    w[0] = (unsigned short)m16;
+                    if (i >= 2) w[-1] = (unsigned short)m16;
+                }
             }
             const int dn = it + 1;
             if (mt == 0) sCount[(it + 2) % 3] = 0;
@@ -579,7 +779,8 @@ __global__ void __launch_bounds__(NT, MINB) k_fill_s16(FillLaunch a)
                         Cb[(dn - 4) * NS + i - 1] = MF_INF;
                     }
                 }
-                if (mt < 16) sRow[(dn & 1) * 16 + mt] = dev_row16(dn, mt, RS);
+                for (int k = mt; k < MF16_NQ * 32; k += MT)
+                    sOff[(dn & 1) * MF16_NQ * 32 + k] = dev_term_off16((&P->s16_td[dn & 1][0][0])[k], k & 31, dn, RS, RW);
             }
             if ((it + 1 - 5) % 5 == 0 && it <= dmax) {   // next iteration runs the DML strip [it, it+4]
                 for (int s = 0; s < 5; s++)
@@ -693,7 +894,7 @@ static cudaError_t configure_fill_bucket()
 {
     cudaError_t e = cudaFuncSetAttribute(k_fill_smem<NS, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FillSmem<NS>::bytes);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_fill_s16<NS, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Fill16Smem<NS>::bytes);
+    return cudaFuncSetAttribute(k_fill_s16<NS, NT, MF16_NWM(NT), MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Fill16Smem<NS>::bytes);
 }
 // function attributes are per device: called once per device of a context (mirfold_open)
 cudaError_t fill_configure_device()
@@ -716,7 +917,7 @@ static cudaError_t launch_fill_bucket(const FillLaunch &a, int first, int count,
     if (a.force_wide) b.flags = nullptr;
     else {
         b.flags = a.flags + first;
-        k_fill_s16<NS, NT, MINB><<<count, NT, smem16, st>>>(b);
+        k_fill_s16<NS, NT, MF16_NWM(NT), MINB><<<count, NT, smem16, st>>>(b);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }

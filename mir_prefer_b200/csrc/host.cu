@@ -80,14 +80,14 @@ struct Device {
     DevParams *dP = nullptr;
     size_t mem_budget = 0;
     // pooled buffers
-    DBuf raw, loci, codes, F, C, M, ring, fillflags, tbcount, tbbase, listoff, startlist, scan_in, scan_out, scan_tmp;
+    DBuf raw, loci, codes, F, C, M, Mp, ring, fillflags, tbcount, tbbase, listoff, startlist, scan_in, scan_out, scan_tmp;
     DBuf slots, tblen, tbstart, tblocus, tbflag, tbenergy, stackscr, fail, ssoff, hitidx;
     DBuf o_start, o_len, o_energy, o_ssoff, o_arena;
     HBuf h_raw, h_loci, h_listoff, h_small, h_out;
     cudaEvent_t ev[12] = {};
     void release()
     {
-        DBuf *all[] = {&raw, &loci, &codes, &F, &C, &M, &ring, &fillflags, &tbcount, &tbbase, &listoff, &startlist, &scan_in,
+        DBuf *all[] = {&raw, &loci, &codes, &F, &C, &M, &Mp, &ring, &fillflags, &tbcount, &tbbase, &listoff, &startlist, &scan_in,
                        &scan_out, &scan_tmp, &slots, &tblen, &tbstart, &tblocus, &tbflag, &tbenergy, &stackscr, &fail,
                        &ssoff, &hitidx, &o_start, &o_len, &o_energy, &o_ssoff, &o_arena};
         for (DBuf *b : all) b->release();
@@ -248,6 +248,12 @@ void build_params(DevParams &P)
     build_s16_schedule(P);
 }
 
+int env_opts()
+{
+    static const int v = getenv("MIRFOLD_OPTS") ? atoi(getenv("MIRFOLD_OPTS")) : 0;
+    return v;
+}
+
 uint64_t cells_of(int n, int L)
 {   // sum_{i=1}^{n-4} (min(n, i+L*) - i - 3)
     const int Ls = std::min(L, n);
@@ -349,7 +355,7 @@ void run_device(Device &D, const char *seqs, const uint64_t *h_off, const std::v
     auto locus_bytes = [&](const Locus &l) {
         const int Ls = std::min(L, l.n), dmax = std::min(Ls, l.n - 1);
         const int stride = band_stride_for(l.n);
-        return (size_t)band_elems(stride, dmax) * 8 + (size_t)stride * MF_RING_PER_STRIDE * 4 + (size_t)l.n * 16 + 4096;
+        return (size_t)band_elems(stride, dmax) * 12 + (size_t)stride * MF_RING_PER_STRIDE * 4 + (size_t)l.n * 16 + 4096;
     };
     {
         size_t b = 0, acc = 0;
@@ -415,6 +421,7 @@ void run_device(Device &D, const char *seqs, const uint64_t *h_off, const std::v
         CK(D.F.ensure(seq_acc * 4));
         CK(D.C.ensure(band_acc * 4));
         CK(D.M.ensure(band_acc * 4));
+        if (!force_wide) CK(D.Mp.ensure(band_acc * 4));
         CK(D.ring.ensure(ring_acc * 4));
         CK(D.tbcount.ensure((size_t)nl * 4));
         CK(D.tbbase.ensure((size_t)(nl + 1) * 8));
@@ -429,8 +436,8 @@ void run_device(Device &D, const char *seqs, const uint64_t *h_off, const std::v
         const LocusDesc *dl = D.loci.as<LocusDesc>();
         CK(launch_prepare(raw_dev, dl, nl, seq_acc, D.codes.as<unsigned char>(), D.F.as<int>(), st));
         CK(cudaEventRecord(D.ev[2], st));
-        FillLaunch fa{dl, nl, max_n, D.codes.as<unsigned char>(), D.C.as<int>(), D.M.as<int>(), D.ring.as<int>(), D.dP, {0, 0, 0, 0, 0},
-                      D.fillflags.as<int>(), force_wide ? 1 : 0};
+        FillLaunch fa{dl, nl, max_n, D.codes.as<unsigned char>(), D.C.as<int>(), D.M.as<int>(), D.ring.as<int>(), D.Mp.as<unsigned int>(),
+                      D.dP, {0, 0, 0, 0, 0}, D.fillflags.as<int>(), force_wide ? 1 : 0, env_opts()};
         {   // loci are sorted by descending n: stride buckets are contiguous
             int k = 0;
             const int lim[3] = {608, 352, 160};
@@ -466,6 +473,7 @@ void run_device(Device &D, const char *seqs, const uint64_t *h_off, const std::v
         tb.ntb = ntb;
         tb.slot_stride = (max_Ls + 4 + 3) & ~3;
         tb.stack_cap = max_Ls / 4 + 16;
+        tb.code_win = (max_Ls + 8 + 15) & ~15;
         CK(D.slots.ensure((size_t)ntb * tb.slot_stride + 16));
         CK(D.tblen.ensure((size_t)ntb * 4 + 16)); CK(D.tbstart.ensure((size_t)ntb * 4 + 16));
         CK(D.tblocus.ensure((size_t)ntb * 4 + 16)); CK(D.tbflag.ensure((size_t)ntb * 4 + 16));
@@ -674,7 +682,7 @@ static int fold_impl(mirfold_ctx *ctx, const char *seqs, const uint64_t *seq_off
                      const char *d_raw, bool download, void *stream, uint32_t flags, mirfold_result **out)
 {
     static const bool env_wide = getenv("MIRFOLD_FORCE_WIDE") != nullptr;   // A/B runs of bench.py
-    const bool force_wide = (flags & MIRFOLD_FLAG_WIDE) != 0 || env_wide;
+    const bool force_wide = (flags & MIRFOLD_FLAG_WIDE) != 0 || env_wide || span_L > MF16_MAX_SPAN;
     if (!ctx || !out || !seq_off || (!seqs && !d_raw && nseq)) return MIRFOLD_ERR_ARG;
     if (span_L < 5 || span_L > MF_MAX_SPAN) { ctx->last_error = "span_L out of range [5, 4096]"; return MIRFOLD_ERR_ARG; }
     *out = nullptr;
@@ -819,15 +827,16 @@ int mirfold_debug_matrices(mirfold_ctx *ctx, const char *seq, uint32_t n, int sp
     d.stride = band_stride_for(d.n);
     const unsigned long long cells = band_elems(d.stride, d.dmax);
     CK(D.raw.ensure(n)); CK(D.loci.ensure(sizeof d)); CK(D.codes.ensure(n + 3)); CK(D.F.ensure((n + 3) * 4));
-    CK(D.C.ensure(cells * 4)); CK(D.M.ensure(cells * 4)); CK(D.ring.ensure((size_t)d.stride * MF_RING_PER_STRIDE * 4));
+    CK(D.C.ensure(cells * 4)); CK(D.M.ensure(cells * 4)); CK(D.Mp.ensure(cells * 4));
+    CK(D.ring.ensure((size_t)d.stride * MF_RING_PER_STRIDE * 4));
     CK(cudaMemcpyAsync(D.raw.p, seq, n, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(D.loci.p, &d, sizeof d, cudaMemcpyHostToDevice, st));
     const LocusDesc *dl = D.loci.as<LocusDesc>();
     CK(launch_prepare(D.raw.as<char>(), dl, 1, n + 3, D.codes.as<unsigned char>(), D.F.as<int>(), st));
     CK(D.fillflags.ensure(4));
     CK(cudaMemsetAsync(D.fillflags.p, 0, 4, st));
-    FillLaunch fa{dl, 1, (int)n, D.codes.as<unsigned char>(), D.C.as<int>(), D.M.as<int>(), D.ring.as<int>(), D.dP, {0, 0, 0, 0, 1},
-                  D.fillflags.as<int>(), (flags & MIRFOLD_FLAG_WIDE) ? 1 : 0};
+    FillLaunch fa{dl, 1, (int)n, D.codes.as<unsigned char>(), D.C.as<int>(), D.M.as<int>(), D.ring.as<int>(), D.Mp.as<unsigned int>(),
+                  D.dP, {0, 0, 0, 0, 1}, D.fillflags.as<int>(), ((flags & MIRFOLD_FLAG_WIDE) || span_L > MF16_MAX_SPAN) ? 1 : 0, env_opts()};
     fa.bucket_first[1] = d.n > 608 ? 1 : 0;
     fa.bucket_first[2] = d.n > 352 ? 1 : 0;
     fa.bucket_first[3] = d.n > 160 ? 1 : 0;

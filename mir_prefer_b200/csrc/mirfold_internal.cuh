@@ -35,6 +35,12 @@
 #define MF16_VALID 20000   /* anything >= this after the min is "no loop"                           */
 #define MF16_GUARD (-32000)
 #define MF16_DBIAS 128
+/* 16-bit fML pairs of the DML strips (k_fill_s16): finite fML in (MF16M_GUARD, ~1300] for spans <= MF16_MAX_SPAN */
+#define MF16M_INF 16383
+#define MF16M_INF2 0x3FFF3FFFu
+#define MF16M_VALID 2700    /* a sum of two finite fML is below this; anything with an INF operand is above */
+#define MF16M_GUARD (-13600)
+#define MF16_MAX_SPAN 1000  /* hairpin extrapolation keeps fML < 1350 up to this span */
 
 struct DevParams {
     int hairpinE[MF_MAX_SPAN + 2];  // by loop size, incl. the lxc*log extrapolation (A.2)
@@ -98,10 +104,12 @@ struct FillLaunch {
     int max_n;
     const unsigned char *codes;
     int *C, *M, *ring;
+    unsigned int *Mp;     // narrow kernel: fML as 16-bit row pairs (same layout as M)
     const DevParams *P;
     int bucket_first[5];  // loci sorted by descending n: [generic | <=608 | <=352 | <=160 | end)
     int *flags;           // per locus: 1 = the 16-bit kernel left its range, redo with the 32-bit kernel
     int force_wide;       // skip the 16-bit kernel (MIRFOLD_FLAG_WIDE)
+    int opts;             // experiment switches (env MIRFOLD_OPTS): bit 0 = no L1 prefetch in the DML strips
 };
 cudaError_t launch_prepare(const char *raw, const LocusDesc *loci, int nloci, unsigned long long total_codes,
                            unsigned char *codes, int *F, cudaStream_t st);
@@ -132,6 +140,7 @@ struct TraceBuffers {
     int *tb_energy;                // ntb
     int *stack_scratch;            // ntb * stack_cap * 2 ints
     int stack_cap;
+    int code_win;                  // bytes of shared memory per traceback warp for the window's codes
     int *fail_flag;                // 1 int
 };
 cudaError_t launch_plan(const TraceBuffers &b, cudaStream_t st);

@@ -129,11 +129,20 @@ __global__ void __launch_bounds__(128) k_traceback(TraceBuffers b)
     const int kidx = (int)(g - b.tb_base[l]);
     const int start = b.tb_start_list[b.list_off[l] + kidx];
     Fold f;
-    f.P = b.P; f.cd = b.codes + L.seq_off; f.C = b.C + L.band_off; f.M = b.M + L.band_off; f.F = b.F + L.seq_off;
+    f.P = b.P; f.C = b.C + L.band_off; f.M = b.M + L.band_off; f.F = b.F + L.seq_off;
     f.n = L.n; f.Ls = L.Ls; f.NS = L.stride;
     const DevParams *__restrict__ P = b.P;
     const int n = L.n;
     const int md = (start == 1) ? L.Ls : L.Ls + 1;   // final backtrack(1, L*) vs backtrack(i+1, L*+1)
+    {   // stage the codes of the window [start-1, min(n, start+md+1)+2] in shared memory (every S/S1 lookup hits it)
+        extern __shared__ unsigned char s_codes[];
+        unsigned char *w = s_codes + (threadIdx.x >> 5) * b.code_win;
+        const unsigned char *src = b.codes + L.seq_off;
+        const int lo = start - 1, hi = min(n + 2, start + md + 3);
+        for (int k = lo + lane; k <= hi; k += 32) w[k - lo] = src[k];
+        f.cd = w - lo;
+        __syncwarp();
+    }
 
     char *st = b.slots + g * (unsigned long long)b.slot_stride;
     const int ndash = min(n - start, md) + 1;
@@ -230,24 +239,39 @@ __global__ void __launch_bounds__(128) k_traceback(TraceBuffers b)
             }
         }
         // "repeat": (i,j) pairs; follow stacks / interior loops until a hairpin or multiloop
+        int cij = f.c(i, j);
         for (;;) {
-            const int cij = f.c(i, j), t = f.type(i, j);
+            const int t = f.type(i, j);
             if (cij == tb_hairpin(f, i, j, t)) break;
             const int d = j - i;
             const int K = min(30, d - 6);
-            int np = 0, nq = 0;
+            int np = 0, nq = 0, ncij = 0;
             bool found = false;
+            if (K >= 0) {   // the stack (p,q) = (i+1,j-1) is the first candidate in reference order: test it alone first
+                const int t2 = f.type(i + 1, j - 1);
+                if (t2) {
+                    const int c2 = f.c(i + 1, j - 1);
+                    if (cij == P->stack[t * 8 + P->rtype[t2]] + c2) {
+                        i++; j--; cij = c2;
+                        if (lane == 0) { st[i - start] = '('; st[j - start] = ')'; }
+                        continue;
+                    }
+                }
+            }
             if (K >= 0) {
                 for (int cb = 0; cb < 496; cb += 32) {
                     const int m = cb + lane;
                     bool ok = false;
-                    int p = 0, q = 0;
+                    int p = 0, q = 0, cpq = 0;
                     if (m < 496) {
                         const int u = P->uv[m][0], v = P->uv[m][1];
                         if (u + v <= K) {
                             p = i + 1 + u; q = j - 1 - v;
                             const int t2 = f.type(p, q);
-                            if (t2) ok = (cij == tb_loop_energy(f, i, j, p, q, t, P->rtype[t2]) + f.c(p, q));
+                            if (t2) {
+                                cpq = f.c(p, q);
+                                ok = (cij == tb_loop_energy(f, i, j, p, q, t, P->rtype[t2]) + cpq);
+                            }
                         }
                     }
                     const unsigned hit = __ballot_sync(FULL, ok);
@@ -255,6 +279,7 @@ __global__ void __launch_bounds__(128) k_traceback(TraceBuffers b)
                         const int src = __ffs(hit) - 1;
                         np = __shfl_sync(FULL, p, src);
                         nq = __shfl_sync(FULL, q, src);
+                        ncij = __shfl_sync(FULL, cpq, src);
                         found = true;
                         break;
                     }
@@ -263,7 +288,7 @@ __global__ void __launch_bounds__(128) k_traceback(TraceBuffers b)
                 }
             }
             if (found) {
-                i = np; j = nq;
+                i = np; j = nq; cij = ncij;
                 if (lane == 0) { st[i - start] = '('; st[j - start] = ')'; }
                 continue;
             }
@@ -329,7 +354,7 @@ cudaError_t launch_traceback(const TraceBuffers &b, cudaStream_t st)
 {
     if (b.ntb == 0) return cudaSuccess;
     const unsigned long long blocks = (b.ntb + 3) / 4;
-    k_traceback<<<(unsigned)blocks, 128, 0, st>>>(b);
+    k_traceback<<<(unsigned)blocks, 128, 4 * (size_t)b.code_win, st>>>(b);   // code_win <= 4112: below the 48 KB default
     return cudaGetLastError();
 }
 
