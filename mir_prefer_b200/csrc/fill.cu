@@ -21,6 +21,7 @@
 #include <cstdlib>
 #include <cstring>
 #include "mirfold_internal.cuh"
+#include "fill_common.cuh"
 
 // ------------------------------------------------------------------------------------ K1
 __global__ void k_prepare(const char *__restrict__ raw, const LocusDesc *__restrict__ loci, int nloci,
@@ -59,50 +60,6 @@ cudaError_t launch_prepare(const char *raw, const LocusDesc *loci, int nloci, un
     if (nloci == 0) return cudaSuccess;
     k_prepare<<<nloci, 128, 0, st>>>(raw, loci, nloci, codes, F);
     return cudaGetLastError();
-}
-
-// ------------------------------------------------------------------------------------ helpers
-__device__ __forceinline__ int warp_min(int v) { return __reduce_min_sync(0xffffffffu, v); }
-
-__device__ __forceinline__ int dev_loop_energy(const DevParams *__restrict__ P, int t, int t2, int n1, int n2, int si1,
-                                               int sj1, int sp1, int sq1)
-{   // A.2 two-loop energy; t2 already rtype'd
-    const int nl = max(n1, n2), ns = min(n1, n2);
-    if (nl == 0) return P->stack[t * 8 + t2];
-    if (ns == 0) {
-        int e = P->bulge[nl];
-        if (nl == 1) return e + P->stack[t * 8 + t2];
-        return e + (t > 2 ? P->TerminalAU : 0) + (t2 > 2 ? P->TerminalAU : 0);
-    }
-    if (ns == 1 && nl == 1) return P->int11[((t * 8 + t2) * 5 + si1) * 5 + sj1];
-    if (ns == 1 && nl == 2) {
-        if (n1 == 1) return P->int21[(((t * 8 + t2) * 5 + si1) * 5 + sq1) * 5 + sj1];
-        return P->int21[(((t2 * 8 + t) * 5 + sq1) * 5 + si1) * 5 + sp1];
-    }
-    if (n1 == 2 && n2 == 2) return P->int22[((((t * 8 + t2) * 5 + si1) * 5 + sp1) * 5 + sq1) * 5 + sj1];
-    return P->internal_loop[n1 + n2] + min(300, (nl - ns) * 50) + P->mismatchI[(t * 5 + si1) * 5 + sj1] +
-           P->mismatchI[(t2 * 5 + sq1) * 5 + sp1];
-}
-
-// hairpin energy of the pair (i,j) of type t; sS/sS1 are 1-based code arrays
-__device__ __forceinline__ int dev_hairpin(const DevParams *__restrict__ P, const unsigned char *sS,
-                                           const unsigned char *sS1, int i, int j, int t)
-{
-    const int s = j - i - 1;
-    int e = P->hairpinE[s];
-    if (s == 4) {
-        int code = 0, ok = 1;
-#pragma unroll
-        for (int k = 0; k < 6; k++) {
-            const int b = sS[i + k];
-            ok &= (b >= 1 && b <= 4);
-            code |= ((b - 1) & 3) << (2 * k);
-        }
-        if (ok) e += P->tetra[code];
-    }
-    if (s == 3) e += (t > 2 ? P->TerminalAU : 0);
-    else e += P->mismatchH[(t * 5 + sS1[i + 1]) * 5 + sS1[j - 1]];
-    return e;
 }
 
 // the seven table-driven two-loops of a typed cell + hairpin + d1 multiloop closing (A.2, A.3)
@@ -167,7 +124,6 @@ __device__ __forceinline__ int dev_fml(const DevParams *__restrict__ P, const un
     return min(m, rD[(d & (MF_RING_DML - 1)) * NS + i - 1]);
 }
 
-__device__ __forceinline__ void dev_prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // phase A: DML for the strip d..d1 from fML diagonals <= d-1.  One (row, part) per thread; `part`
 // splits the e-range when the strip has fewer rows than the CTA has threads.
@@ -495,14 +451,6 @@ __global__ void __launch_bounds__(NT, MINB) k_fill_smem(FillLaunch a)
 // bank class l (DevParams::s16_*), so a typed cell costs 10 conflict-free LDS + 10 VIADDMNMX.S16x2 per
 // lane (8 generic, 2 bulge), one packed combine and one redux.  Exact while c > MF16_GUARD; otherwise
 // the locus is flagged for the 32-bit kernel.
-// shared-memory load from an absolute 32-bit shared address (volatile: never hoisted or merged)
-__device__ __forceinline__ unsigned dev_lds(unsigned addr)
-{
-    unsigned w;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(addr));
-    return w;
-}
-
 #ifndef MF16_NWM
 #define MF16_NWM(NT) (((NT) / 32 * 3 + 4) / 8)   /* fML/list warps of the narrow kernel: 6 of 16, 5 of 12, 3 of 8 */
 #endif
@@ -541,7 +489,6 @@ __device__ __forceinline__ int dev_ring16_get(const unsigned int *ring, int RS, 
     const short *w = (const short *)(ring + (pp % MF16_NPS) * RS + ((MF16_SKEW * pp) & 31) + x);
     return w[dd & 1];
 }
-__device__ __forceinline__ int dev_rtype(int t) { return t ? (((t - 1) ^ 1) + 1) : 0; }   // {0,2,1,4,3,6,5}
 
 // The seven table-driven two-loops + hairpin + d1 multiloop closing of a typed cell, narrow kernel:
 // branch-free (all lookups of the seven loops are independent and overlap) and with c(p,q) read from
@@ -903,6 +850,7 @@ cudaError_t fill_configure_device()
     if ((e = configure_fill_bucket<608, 512, 2>()) != cudaSuccess) return e;
     if ((e = configure_fill_bucket<352, 384, 3>()) != cudaSuccess) return e;
     if ((e = configure_fill_bucket<160, 256, 4>()) != cudaSuccess) return e;
+    if ((e = fill_narrow_configure_device()) != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_fill_generic<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 }
 
@@ -917,8 +865,11 @@ static cudaError_t launch_fill_bucket(const FillLaunch &a, int first, int count,
     if (a.force_wide) b.flags = nullptr;
     else {
         b.flags = a.flags + first;
-        k_fill_s16<NS, NT, MF16_NWM(NT), MINB><<<count, NT, smem16, st>>>(b);
-        cudaError_t e = cudaGetLastError();
+        cudaError_t e;
+        if (a.opts & 4) {   // previous narrow kernel (A/B runs)
+            k_fill_s16<NS, NT, MF16_NWM(NT), MINB><<<count, NT, smem16, st>>>(b);
+            e = cudaGetLastError();
+        } else e = launch_fill_narrow(b, NS == 608 ? 0 : NS == 352 ? 1 : 2, st);
         if (e != cudaSuccess) return e;
     }
     k_fill_smem<NS, NT, MINB><<<count, NT, smem, st>>>(b);   // 32-bit kernel: all loci if forced, else only flagged ones
