@@ -57,4 +57,9 @@ __device__ __forceinline__ unsigned dev_lds(unsigned addr)
     return w;
 }
 
+// two adjacent 16-bit shared-memory stores at an absolute shared address
+__device__ __forceinline__ void dev_sts16x2(unsigned addr, int a, int b)
+{
+    asm volatile("st.shared.u16 [%0], %1;\n\tst.shared.u16 [%0+2], %2;" ::"r"(addr), "h"((unsigned short)a), "h"((unsigned short)b) : "memory");
+}
 __device__ __forceinline__ int dev_rtype(int t) { return t ? (((t - 1) ^ 1) + 1) : 0; }   // {0,2,1,4,3,6,5}

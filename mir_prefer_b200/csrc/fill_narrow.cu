@@ -28,7 +28,8 @@
 
 #define MFQ_NPS 16     /* pair slots of the ring: rows X-32..X-3 are read while X-2, X-1 are written */
 #define MFQ_PC 8       /* typed cells per P item                                                       */
-#define MFQ_EPART 48   /* split positions per A item                                                   */
+#define MFQ_EPART 32   /* split positions per bulk DML item                                            */
+#define MFQ_SW 8       /* DML strip width (diagonals per bulk pass)                                    */
 #define FULLMASK 0xffffffffu
 
 template <int NS>
@@ -173,13 +174,17 @@ __global__ void __launch_bounds__(NT, MINB) k_fill_q16(FillLaunch a)
     unsigned char *sS1 = sS + NS + 8;
     unsigned char *sPair = sS1 + NS + 8;
     __shared__ int sCnt[4][2];    // typed cells per listed diagonal, slot (X/2) & 3
-    __shared__ int sNext[2][2];   // queue heads, [step parity][queue]
+    __shared__ int sNext[2][4];   // queue heads, [step parity][queue]
     __shared__ int sFlag;
 
     const LocusDesc L = a.loci[blockIdx.x];
-    const int n = L.n, Ls = L.Ls, dmax = L.dmax;
     const DevParams *__restrict__ P = a.P;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    // Everything that steers a warp through the queues goes through redux.sync: its result lives in a
+    // uniform register, so the compiler knows the branches are warp-uniform (no divergence handling, and
+    // the P loop's ring loads become LDS [R + UR]).
+    const int wid = __reduce_min_sync(FULLMASK, tid >> 5);
+    const int n = __reduce_min_sync(FULLMASK, L.n), Ls = __reduce_min_sync(FULLMASK, L.Ls), dmax = __reduce_min_sync(FULLMASK, L.dmax);
     const int AUp = P->TerminalAU;
 
     for (int k = tid; k < NS + 8; k += NT) {
@@ -191,7 +196,7 @@ __global__ void __launch_bounds__(NT, MINB) k_fill_q16(FillLaunch a)
     for (int k = tid; k < 200; k += NT) sMM[k] = P->mismatchI[k];
     if (tid < 64) sPair[tid] = P->pair[tid];
     if (tid < 8) (&sCnt[0][0])[tid] = 0;
-    if (tid < 4) (&sNext[0][0])[tid] = 0;
+    if (tid < 8) (&sNext[0][0])[tid] = 0;
     if (tid == 0) sFlag = 0;
 
     int *Cb = a.C + L.band_off;
@@ -220,57 +225,60 @@ __global__ void __launch_bounds__(NT, MINB) k_fill_q16(FillLaunch a)
     for (int X = 4; X - 4 <= dmax; X += 2) {
         const int h = X >> 1;
         // ---- item counts of this step (uniform over the CTA)
-        const int cP0 = (X <= dmax) ? sCnt[h & 3][0] : 0;
-        const int cP1 = (X + 1 <= dmax) ? sCnt[h & 3][1] : 0;
-        const int cT0 = (X - 2 >= 4 && X - 2 <= dmax) ? sCnt[(h - 1) & 3][0] : 0;
-        const int cT1 = (X - 2 >= 4 && X - 1 <= dmax) ? sCnt[(h - 1) & 3][1] : 0;
+        const int cP0 = __reduce_min_sync(FULLMASK, (X <= dmax) ? sCnt[h & 3][0] : 0);
+        const int cP1 = __reduce_min_sync(FULLMASK, (X + 1 <= dmax) ? sCnt[h & 3][1] : 0);
+        const int cT0 = __reduce_min_sync(FULLMASK, (X - 2 >= 4 && X - 2 <= dmax) ? sCnt[(h - 1) & 3][0] : 0);
+        const int cT1 = __reduce_min_sync(FULLMASK, (X - 2 >= 4 && X - 1 <= dmax) ? sCnt[(h - 1) & 3][1] : 0);
         const int nP0 = (cP0 + MFQ_PC - 1) / MFQ_PC, nP1 = (cP1 + MFQ_PC - 1) / MFQ_PC;
-        const int hiD = min(X, dmax);                                   // newest DML diagonal of this step
-        const bool doA = (X - 1 >= 9 && X - 1 <= dmax), doB = (doA && X <= dmax);
-        const int nparts = doA ? (hiD - 8 + MFQ_EPART - 1) / MFQ_EPART : 0;
-        const int nchunkA = doA ? ((n - (X - 1) + 1) / 2 + 31) / 32 : 0;
+        // DML: step X with (X-10) % SW == 0 computes the bulk of the strip X-1 .. X+SW-2 (all split terms whose
+        // two fML operands lie on diagonals <= X-5, the newest complete one); every other step finalises its
+        // own two diagonals X-1, X with the few terms that involve the diagonals completed since.
+        const int sA = (X >= 10 && X - 1 <= dmax) ? ((X - 10) & (MFQ_SW - 1)) : -1;
+        const int nparts = (sA == 0) ? (X - 8 + MFQ_EPART - 1) / MFQ_EPART : 1;
+        const int nchunkA = (sA >= 0) ? ((n - (X - 1) + 1) / 2 + 31) / 32 : 0;
         const int nA = nparts * nchunkA;
         const int nR = (n - max(4, X - 4) + 30) / 31;
         const int nT0 = (cT0 + 31) / 32, nT1 = (cT1 + 31) / 32;
         const int bA = nA, bR = bA + nR, bT0 = bR + nT0, bT1 = bT0 + nT1, total2 = bT1 + 1;
-        const int totalP = nP0 + nP1;
         const int lbP = h % 3, lbT = (h + 2) % 3, lbL = (h + 1) % 3;
 
-        unsigned off[MF16_NQ], cst[MF16_NQ], mk[MF16_NMK];
-        int curpar = -1;
-
-        for (int pass = 0; pass < 2; pass++) {
-            const int q = (wid < NWP ? 0 : 1) ^ pass;
-            const int total = q ? total2 : totalP;
-            for (;;) {
-                int k = 0;
-                if (lane == 0) k = atomicAdd(&sNext[h & 1][q], 1);
-                k = __shfl_sync(FULLMASK, k, 0);
-                if (k >= total) break;
-                if (q == 0) {
+        // queues: 0 = P items of diagonal X, 1 = P items of diagonal X+1, 2 = everything else.  The first
+        // half of the warps takes them in the order 0,1,2, the other half 2,0,1.
+        for (int pass = 0; pass < 3; pass++) {
+            const int q = (wid < NWP) ? pass : (pass == 0 ? 2 : pass - 1);
+            if (q < 2) {
+                const int par = q;
+                const int cnt = par ? cP1 : cP0;
+                const int total = par ? nP1 : nP0;
+                if (__reduce_min_sync(FULLMASK, *(volatile int *)&sNext[h & 1][q]) >= total) continue;
+                // per-lane word-term addresses (bytes, shared window), packed constants and masks of this parity
+                unsigned off[MF16_NQ], cst[MF16_NQ], mk[MF16_NMK];
+#pragma unroll
+                for (int qq = 0; qq < MF16_NQ; qq++) {
+                    off[qq] = smem_base + 4u * sOff[(((h & 1) * 2 + par) * MF16_NQ + qq) * 32 + lane];
+                    asm("" : "+r"(off[qq]));   // keep the byte address as one register (no re-association in the cell loop)
+                    cst[qq] = P->s16_cst[par][qq][lane];
+                }
+#pragma unroll
+                for (int qq = 0; qq < MF16_NMK; qq++) mk[qq] = P->s16_mk[par][qq][lane];
+                unsigned listb = smem_base + 4u * (unsigned)(SM::oList + (lbP * 2 + par) * NS);       // shared byte addresses
+                unsigned myb = smem_base + 4u * (unsigned)SM::oMy + 2u * (unsigned)(((h & 1) * 2 + par) * NS);
+                asm volatile("" : "+r"(listb), "+r"(myb));   // opaque: kept in registers, not rematerialised in the cell loop
+                for (;;) {
+                    int k = 0;
+                    if (lane == 0) k = atomicAdd(&sNext[h & 1][q], 1);
+                    k = __reduce_max_sync(FULLMASK, k);
+                    if (k >= total) break;
                     // ------------------------------------------------------------ P item
-                    const int par = (k >= nP0) ? 1 : 0;
-                    const int d = X + par;
-                    const int cnt = par ? cP1 : cP0;
-                    const int c0 = (par ? k - nP0 : k) * MFQ_PC, c1 = min(cnt, c0 + MFQ_PC);
-                    if (curpar != par) {
-                        curpar = par;
-#pragma unroll
-                        for (int qq = 0; qq < MF16_NQ; qq++) {
-                            off[qq] = smem_base + 4u * sOff[(((h & 1) * 2 + par) * MF16_NQ + qq) * 32 + lane];
-                            asm("" : "+r"(off[qq]));   // keep the byte address as one register (no re-association in the cell loop)
-                            cst[qq] = P->s16_cst[par][qq][lane];
-                        }
-#pragma unroll
-                        for (int qq = 0; qq < MF16_NMK; qq++) mk[qq] = P->s16_mk[par][qq][lane];
-                    }
-                    const unsigned int *list = sList + (lbP * 2 + par) * NS;
-                    short *my = sMy + ((h & 1) * 2 + par) * NS;
-                    (void)d;
+                    const int c0 = k * MFQ_PC, c1 = __reduce_min_sync(FULLMASK, min(cnt, c0 + MFQ_PC));
                     for (int c = c0; c < c1; c += 2) {
-                        const bool two = (c + 1 < c1);
-                        const unsigned ea = list[c], eb = list[two ? c + 1 : c];
-                        const unsigned ia = ea & 0xffffu, ib = eb & 0xffffu;
+                        // an odd tail evaluates its last cell twice (same value stored to my[c] and my[c+1], which is unused)
+                        const unsigned ea = dev_lds(listb + 4u * c), eb = dev_lds(listb + 4u * min(c + 1, c1 - 1));
+                        __syncwarp();   // tells the compiler the warp is converged: redux without a divergence check
+                        // the cell's byte offset is warp-uniform: redux puts it into a uniform register and the
+                        // ten loads become LDS [R + UR] with no per-load address arithmetic
+                        const unsigned ia = (unsigned)__reduce_min_sync(FULLMASK, (int)(ea & 0xffffu));
+                        const unsigned ib = (unsigned)__reduce_min_sync(FULLMASK, (int)(eb & 0xffffu));
                         unsigned aG = MF16_INF2, aB = MF16_INF2, bG = MF16_INF2, bB = MF16_INF2;
 #pragma unroll
                         for (int qq = 0; qq < MF16_NQG; qq++) {
@@ -296,55 +304,83 @@ __global__ void __launch_bounds__(NT, MINB) k_fill_q16(FillLaunch a)
                         int vb = min((int)(short)(accb & 0xffffu), (int)accb >> 16);
                         va = warp_min(va);
                         vb = warp_min(vb);
-                        if (lane == 0) {
-                            my[c] = (short)va;
-                            if (two) my[c + 1] = (short)vb;
-                        }
+                        if (lane == 0) dev_sts16x2(myb + 2u * c, va, vb);
                     }
-                } else if (k < bA) {
-                    // ------------------------------------------------------------ A item: DML(X-1), DML(X)
+                }
+                continue;
+            }
+            for (;;) {
+                int k = 0;
+                if (lane == 0) k = atomicAdd(&sNext[h & 1][2], 1);
+                k = __reduce_max_sync(FULLMASK, k);
+                if (k >= total2) break;
+                if (k < bA) {
+                    // ------------------------------------------------------------ A item
                     const int chunk = k / nparts, part = k - chunk * nparts;
                     const int i = 2 * (chunk * 32 + lane) + 1;       // rows i (lo half) and i+1 (hi half)
-                    const int da = X - 1;
-                    if (i <= n - da) {
-                        const int e0 = 4 + part * MFQ_EPART, e1 = min(hiD - 5, e0 + MFQ_EPART - 1);
-                        const unsigned int *pa = Mp + (e0 - 4) * NS + (i - 1);        // fML(i, i+e) | fML(i+1, i+1+e)
-                        const unsigned int *pb = Mp + (da - 5 - e0) * NS + (i + e0);  // fML(i+e+1, i+da) | fML(i+e+2, i+1+da); +NS: X
-                        unsigned accA = MF16M_INF2, accB = MF16M_INF2;
-                        const int emain = min(e1, da - 5);
-                        int e = e0;
-                        if (doB) {
-#pragma unroll 4
+                    if (i <= n - (X - 1)) {
+                        if (sA == 0) {
+                            // bulk of the strip: row s is diagonal X-1+s and takes the split positions e in
+                            // [max(4, s+3), X-5] (row 0: X-6), i.e. fML(i,i+e) + fML(i+e+1, i+X-1+s) with both spans <= X-5
+                            const int e0 = 4 + part * MFQ_EPART, e1 = min(X - 5, e0 + MFQ_EPART - 1);
+                            const unsigned int *pa = Mp + (e0 - 4) * NS + (i - 1);       // fML(i, i+e) | fML(i+1, i+1+e)
+                            const unsigned int *pb = Mp + (X - 6 - e0) * NS + (i + e0);  // row s: + s*NS
+                            unsigned acc[MFQ_SW];
+#pragma unroll
+                            for (int sr = 0; sr < MFQ_SW; sr++) acc[sr] = MF16M_INF2;
+                            int e = e0;
+                            for (; e <= min(e1, MFQ_SW + 1); e++) {                      // head: rows start at e = s+3
+                                const unsigned av = pa[0];
+#pragma unroll
+                                for (int sr = 0; sr < MFQ_SW; sr++)
+                                    if (e >= sr + 3 && (sr > 0 || e <= X - 6)) acc[sr] = __viaddmin_s16x2(av, pb[sr * NS], acc[sr]);
+                                pa += NS;
+                                pb -= (NS - 1);
+                            }
+                            const int emain = min(e1, X - 6);
+#pragma unroll 2
                             for (; e <= emain; e++) {
                                 const unsigned av = pa[0];
-                                accA = __viaddmin_s16x2(av, pb[0], accA);
-                                accB = __viaddmin_s16x2(av, pb[NS], accB);
+#pragma unroll
+                                for (int sr = 0; sr < MFQ_SW; sr++) acc[sr] = __viaddmin_s16x2(av, pb[sr * NS], acc[sr]);
                                 pa += NS;
                                 pb -= (NS - 1);
                             }
-                            if (e <= e1) accB = __viaddmin_s16x2(pa[0], pb[NS], accB);   // e = X-5: diagonal X only
-                        } else {
-#pragma unroll 4
-                            for (; e <= emain; e++) {
-                                accA = __viaddmin_s16x2(pa[0], pb[0], accA);
-                                pa += NS;
-                                pb -= (NS - 1);
+                            if (e <= e1) {                                               // e = X-5: not row 0
+                                const unsigned av = pa[0];
+#pragma unroll
+                                for (int sr = 1; sr < MFQ_SW; sr++) acc[sr] = __viaddmin_s16x2(av, pb[sr * NS], acc[sr]);
                             }
-                        }
-                        int *dA = &rD[(da & (MF_RING_DML - 1)) * NS + (i - 1)];
-                        int *dB = &rD[((da + 1) & (MF_RING_DML - 1)) * NS + (i - 1)];
-                        const int alo = (int)(short)(accA & 0xffffu), ahi = (int)accA >> 16;
-                        const int blo = (int)(short)(accB & 0xffffu), bhi = (int)accB >> 16;
-                        if (nparts == 1) {
-                            if (alo < MF16M_VALID) dA[0] = alo;
-                            if (i + 1 <= n - da && ahi < MF16M_VALID) dA[1] = ahi;
-                            if (doB && i <= n - da - 1 && blo < MF16M_VALID) dB[0] = blo;
-                            if (doB && i + 1 <= n - da - 1 && bhi < MF16M_VALID) dB[1] = bhi;
+#pragma unroll
+                            for (int sr = 0; sr < MFQ_SW; sr++) {
+                                const int dd = X - 1 + sr;
+                                if (dd <= dmax) {
+                                    int *dst = &rD[(dd & (MF_RING_DML - 1)) * NS + (i - 1)];
+                                    const int lo = (int)(short)(acc[sr] & 0xffffu), hi = (int)acc[sr] >> 16;
+                                    if (i <= n - dd && lo < MF16M_VALID) atomicMin(dst, lo);
+                                    if (i + 1 <= n - dd && hi < MF16M_VALID) atomicMin(dst + 1, hi);
+                                }
+                            }
                         } else {
-                            if (alo < MF16M_VALID) atomicMin(dA, alo);
-                            if (i + 1 <= n - da && ahi < MF16M_VALID) atomicMin(dA + 1, ahi);
-                            if (doB && i <= n - da - 1 && blo < MF16M_VALID) atomicMin(dB, blo);
-                            if (doB && i + 1 <= n - da - 1 && bhi < MF16M_VALID) atomicMin(dB + 1, bhi);
+                            // finalise diagonals X-1, X: the strip's bulk (step X - sA) stopped at fML diagonal D
+                            const int D = X - sA - 5;
+#pragma unroll
+                            for (int r = 0; r < 2; r++) {
+                                const int dd = X - 1 + r;
+                                if (dd <= dmax) {
+                                    const int eh = dd - 2 - D;
+                                    unsigned acc = MF16M_INF2;
+                                    for (int e = 4; e <= eh; e++) {
+                                        // fML(i,i+e) + fML(i+e+1,i+dd)   and the mirrored split e' = dd-e-1
+                                        acc = __viaddmin_s16x2(Mp[(e - 4) * NS + i - 1], Mp[(dd - e - 5) * NS + i + e], acc);
+                                        acc = __viaddmin_s16x2(Mp[(dd - e - 5) * NS + i - 1], Mp[(e - 4) * NS + i + dd - e - 1], acc);
+                                    }
+                                    int *dst = &rD[(dd & (MF_RING_DML - 1)) * NS + (i - 1)];
+                                    const int lo = (int)(short)(acc & 0xffffu), hi = (int)acc >> 16;
+                                    if (i <= n - dd && lo < MF16M_VALID) atomicMin(dst, lo);
+                                    if (i + 1 <= n - dd && hi < MF16M_VALID) atomicMin(dst + 1, hi);
+                                }
+                            }
                         }
                     }
                 } else if (k < bR) {
@@ -379,10 +415,10 @@ __global__ void __launch_bounds__(NT, MINB) k_fill_q16(FillLaunch a)
                                 }
                             }
                         }
-                        // DML rows the A items of the next step accumulate into
-                        if (i <= n - (X + 1)) {
-                            rD[((X + 1) & (MF_RING_DML - 1)) * NS + i - 1] = MF_INF;
-                            rD[((X + 2) & (MF_RING_DML - 1)) * NS + i - 1] = MF_INF;
+                        // DML rows of the strip whose bulk the next step computes
+                        if (X >= 8 && ((X - 8) & (MFQ_SW - 1)) == 0 && i <= n - (X + 1)) {
+#pragma unroll
+                            for (int sr = 0; sr < MFQ_SW; sr++) rD[((X + 1 + sr) & (MF_RING_DML - 1)) * NS + i - 1] = MF_INF;
                         }
                     }
                     // typed lists of the diagonals the P items of the next step search
@@ -429,10 +465,8 @@ __global__ void __launch_bounds__(NT, MINB) k_fill_q16(FillLaunch a)
                     // ------------------------------------------------------------ misc: next step's term offsets, counters
                     for (int kk = lane; kk < 2 * MF16_NQ * 32; kk += 32)
                         sOff[((h + 1) & 1) * 2 * MF16_NQ * 32 + kk] = (unsigned short)q_term_off<NS>((&P->s16_td[0][0][0])[kk], kk & 31, h);
-                    if (lane < 2) {
-                        sNext[(h + 1) & 1][lane] = 0;
-                        sCnt[(h + 2) & 3][lane] = 0;
-                    }
+                    if (lane < 4) sNext[(h + 1) & 1][lane] = 0;
+                    if (lane < 2) sCnt[(h + 2) & 3][lane] = 0;
                 }
             }
         }

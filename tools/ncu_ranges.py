@@ -3,7 +3,10 @@
 usage: ncu -i rep --page source --csv --print-source cuda,sass | python tools/ncu_ranges.py name:lo-hi[,lo-hi] ..."""
 import collections, csv, sys
 ranges = []
+FILE = "fill.cu"
 for a in sys.argv[1:]:
+    if a.startswith("file="):
+        FILE = a[5:]; continue
     name, spec = a.split(":")
     for part in spec.split(","):
         lo, hi = part.split("-")
@@ -29,8 +32,8 @@ for r in rows:
     except ValueError:
         continue
     key = "other:" + fname
-    if fname == "fill.cu":
-        key = "fill.cu:unassigned"
+    if fname == FILE:
+        key = FILE + ":unassigned"
         for name, lo, hi in ranges:
             if lo <= ln <= hi:
                 key = name; break
