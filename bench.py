@@ -32,8 +32,14 @@ UNIT = "nt/s"
 SPAN = 300
 
 
+WORKLOADS = {   # name -> (length law, base seed, BASELINE configs index)
+    "parity": ("parity", 1001, 1), "arabidopsis": ("arabidopsis", 1002, 2), "long": ("long", 1003, 3), "sweep": ("sweep", 1004, 4)}
+WORKLOAD = "parity"
+
+
 def workload(rank, nloci):
-    return synth_loci(1001 + rank, nloci, "parity")
+    law, seed, _ = WORKLOADS[WORKLOAD]
+    return synth_loci(seed + rank, nloci, law)
 
 
 # ---------------------------------------------------------------------------------- work model
@@ -221,6 +227,7 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- kernel-resident timing (value): inputs in HBM, results stay in HBM
     fill_ms, dev_ms, launches, tracebacks, cells = [], [], 0, 0, 0
+    stage = {"ms_fill": 0.0, "ms_f3": 0.0, "ms_trace": 0.0}
     for _ in range(args.warmup):
         mf.fold_device(d_buf.data_ptr(), off, SPAN, stream=stream).close()
     sampler = ClockSampler(local_rank)
@@ -231,6 +238,9 @@ def run_ours(args, rank, world, local_rank):
     for _ in range(args.steps):
         r = mf.fold_device(d_buf.data_ptr(), off, SPAN, stream=stream)
         fill_ms.append(r.stats["ms_fill"]); dev_ms.append(r.stats["ms_device"])
+        for k in stage:
+            stage[k] += r.stats[k] / args.steps
+        n_chunks = r.stats["n_chunks"]
         launches += r.stats["kernel_launches"]; tracebacks = r.stats["tracebacks"]; cells = r.stats["cells"]
         r.close()
     e1.record()
@@ -277,14 +287,17 @@ def run_ours(args, rank, world, local_rank):
             "metric": METRIC, "value": nt_all * args.steps / t_dev, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": {"workload": "parity-10k (BASELINE configs[1]): %d loci/GPU, 300-600 nt, GC 0.40, embedded hairpins, L=300"
-                                   % args.loci, "span_L": SPAN, "loci_per_gpu": args.loci, "nt_per_gpu": nt,
+            "config": {"workload": ("parity-10k (BASELINE configs[1]): %d loci/GPU, 300-600 nt, GC 0.40, embedded hairpins, L=300"
+                                    % args.loci) if WORKLOAD == "parity" and SPAN == 300 else
+                                   "%s law (BASELINE configs[%d]), %d loci/GPU, L=%d" % (WORKLOAD, WORKLOADS[WORKLOAD][2], args.loci, SPAN),
+                       "span_L": SPAN, "loci_per_gpu": args.loci, "nt_per_gpu": nt,
                        "dp_cells_per_gpu": int(cells), "cache": "inputs+band workspace (%.1f GB) far larger than L2; no flush needed"
                                    % (band_bytes / 1e9), "tracebacks_per_step": int(tracebacks)},
             "dp_cells_per_s": cells_all * args.steps / t_dev,
             "e2e": {"value": nt_all * args.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * t_e2e / args.steps, "hits_per_step": int(nhits)},
             "gpu_launches": int(launches),
+            "stage_ms": dict(stage, chunks=int(n_chunks)),
             "clocks": clocks,
             "roofline": {"bound": "int32-issue", "kernel": "k_fill", "achieved": achieved / 1e12, "peak": peak / 1e12,
                          "unit": "Tterm/s (1 min-plus term = 1 add + 1 min)", "frac": achieved / peak,
@@ -322,7 +335,12 @@ def main():
     ap.add_argument("--loci", type=int, default=10000, help="loci per GPU (BASELINE configs[1]: 10000)")
     ap.add_argument("--ref-loci-per-core", type=int, default=24)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--workload", default="parity", choices=sorted(WORKLOADS),
+                    help="length law of SURVEY 8(d); the bench line of record is the default (parity-10k)")
+    ap.add_argument("--span", type=int, default=300, help="RNALfold -L (default 300)")
     args = ap.parse_args()
+    global WORKLOAD, SPAN
+    WORKLOAD, SPAN = args.workload, args.span
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

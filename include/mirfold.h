@@ -70,6 +70,7 @@ typedef struct mirfold_stats {
     uint64_t h2d_bytes, d2h_bytes;
     int32_t n_devices;
     int32_t n_chunks;
+    uint64_t fill_units;  /* CTAs of the band fill: one per locus, one per 608-nt tile of a longer locus */
 } mirfold_stats;
 
 /* Result of folding `nseq` records.  Hit order inside a record == RNALfold print order. */

@@ -25,7 +25,8 @@ class Stats(C.Structure):
     _fields_ = [("ms_total", C.c_double), ("ms_h2d", C.c_double), ("ms_fill", C.c_double), ("ms_f3", C.c_double),
                 ("ms_trace", C.c_double), ("ms_d2h", C.c_double), ("ms_device", C.c_double),
                 ("nt", C.c_uint64), ("cells", C.c_uint64), ("tracebacks", C.c_uint64), ("kernel_launches", C.c_uint64),
-                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("n_devices", C.c_int32), ("n_chunks", C.c_int32)]
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("n_devices", C.c_int32), ("n_chunks", C.c_int32),
+                ("fill_units", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

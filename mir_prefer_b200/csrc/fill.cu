@@ -866,10 +866,11 @@ static cudaError_t launch_fill_bucket(const FillLaunch &a, int first, int count,
     else {
         b.flags = a.flags + first;
         cudaError_t e;
-        if (a.opts & 4) {   // previous narrow kernel (A/B runs)
+        if (a.opts & 4) e = launch_fill_narrow(b, NS == 608 ? 0 : NS == 352 ? 1 : 2, st);   // task-queue variant (A/B runs; 8 % slower, r01 s5)
+        else {
             k_fill_s16<NS, NT, MF16_NWM(NT), MINB><<<count, NT, smem16, st>>>(b);
             e = cudaGetLastError();
-        } else e = launch_fill_narrow(b, NS == 608 ? 0 : NS == 352 ? 1 : 2, st);
+        }
         if (e != cudaSuccess) return e;
     }
     k_fill_smem<NS, NT, MINB><<<count, NT, smem, st>>>(b);   // 32-bit kernel: all loci if forced, else only flagged ones
@@ -957,7 +958,7 @@ __global__ void __launch_bounds__(128) k_f3(const LocusDesc *__restrict__ loci, 
                     const int ci = cd[i], si = ci & 7, s1i = ci >> 4, si1 = cd[i + 1] & 7;
                     int j = i + DS;
                     int cj = cd[j], f1 = F[j + 1];
-                    const int *pa = C + (DS - 4) * NS + (i - 1);   // C(i, i+d)
+                    const int *pa = C + band_row_base(L, i) + (DS - 4) * NS;   // C(i, i+d), in row i's owner tile
                     for (int d = DS; d <= dend; d++, j++, pa += NS) {
                         const int cj1 = cd[j + 1], f2 = F[j + 2];
                         const int cA = pa[0], cB = pa[1 - NS];      // C(i+1, j) sits one diagonal down, one row up
@@ -975,20 +976,21 @@ __global__ void __launch_bounds__(128) k_f3(const LocusDesc *__restrict__ loci, 
         }
         for (int i = ihi; i >= ilo; i--) {
             const int d = lane, j = i + d;
+            const int *Ci = C + band_row_base(L, i);   // row i of its owner tile; (i+1, j) is one diagonal down, one row up
             const int f2 = __shfl_down_sync(0xffffffffu, Fw, 1);
             const int ci = cd[i], si = ci & 7, s1i = ci >> 4, si1 = cd[i + 1] & 7;
             int best = MF_INF;
             if (d >= 4 && d < DS && d <= Ls && j <= n - 1) {
-                const int cA = C[(d - 4) * NS + (i - 1)];
-                const int cB = (d >= 5) ? C[(d - 5) * NS + i] : MF_INF;
+                const int cA = Ci[(d - 4) * NS];
+                const int cB = (d >= 5) ? Ci[(d - 5) * NS + 1] : MF_INF;
                 best = dev_f3_term(sPair, sD3, sD5, AUp, si, s1i, si1, cd[j] & 7, cd[j + 1] >> 4, d, Ls, cA, cB, Fw, f2);
             }
             if (lane == 31 && n <= i + Ls) {   // j == n: no f3 / dangle3 terms
                 const int dn = n - i, sj = cd[n] & 7;
                 int t = (dn < Ls) ? sPair[si * 8 + sj] : 0;
-                if (t) best = min(best, C[(dn - 4) * NS + (i - 1)] + (t > 2 ? AUp : 0));
+                if (t) best = min(best, Ci[(dn - 4) * NS] + (t > 2 ? AUp : 0));
                 t = (dn - 1 >= 4) ? sPair[si1 * 8 + sj] : 0;
-                if (t) best = min(best, C[(dn - 5) * NS + i] + sD5[t * 5 + s1i] + (t > 2 ? AUp : 0));
+                if (t) best = min(best, Ci[(dn - 5) * NS + 1] + sD5[t * 5 + s1i] + (t > 2 ? AUp : 0));
             }
             best = warp_min(best);
             const int g = __shfl_sync(0xffffffffu, gout, i - ilo);
@@ -1002,59 +1004,11 @@ __global__ void __launch_bounds__(128) k_f3(const LocusDesc *__restrict__ loci, 
     }
 }
 
-// previous one-warp-per-locus version (strided band reads); kept selectable with MIRFOLD_F3=v1 for A/B runs
-__global__ void __launch_bounds__(128) k_f3_v1(const LocusDesc *__restrict__ loci, int nloci,
-                                            const unsigned char *__restrict__ codes, const int *__restrict__ Call,
-                                            int *__restrict__ Fall, const DevParams *__restrict__ P)
-{
-    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (w >= nloci) return;
-    const LocusDesc L = loci[w];
-    const int n = L.n, Ls = L.Ls, NS = L.stride;
-    const unsigned char *__restrict__ cd = codes + L.seq_off;
-    const int *__restrict__ C = Call + L.band_off;
-    int *F = Fall + L.seq_off;
-    const int AUp = P->TerminalAU;
-    for (int i = n - 4; i >= 1; i--) {
-        int best = MF_INF;
-        const int si = cd[i] & 7, s1i = cd[i] >> 4, si1 = cd[i + 1] & 7;
-        const int jend = min(n - 1, i + Ls);
-        for (int j = i + 4 + lane; j <= jend; j += 32) {
-            const int d = j - i;
-            const int cj = cd[j], cj1 = cd[j + 1];
-            const int sj = cj & 7, s1j1 = cj1 >> 4;
-            const int f1 = F[j + 1], f2 = F[j + 2];
-            int t = (d < Ls) ? P->pair[si * 8 + sj] : 0;
-            if (t) {
-                const int e = C[(d - 4) * NS + (i - 1)] + (t > 2 ? AUp : 0);
-                best = min(best, min(e + f1, e + P->dangle3[t * 5 + s1j1] + f2));
-            }
-            t = (d - 1 >= 4) ? P->pair[si1 * 8 + sj] : 0;
-            if (t) {
-                const int e = C[(d - 5) * NS + i] + P->dangle5[t * 5 + s1i] + (t > 2 ? AUp : 0);
-                best = min(best, min(e + f1, e + P->dangle3[t * 5 + s1j1] + f2));
-            }
-        }
-        if (lane == 0 && n <= i + Ls) {
-            const int d = n - i, sj = cd[n] & 7;
-            int t = (d < Ls) ? P->pair[si * 8 + sj] : 0;
-            if (t) best = min(best, C[(d - 4) * NS + (i - 1)] + (t > 2 ? AUp : 0));
-            t = (d - 1 >= 4) ? P->pair[si1 * 8 + sj] : 0;
-            if (t) best = min(best, C[(d - 5) * NS + i] + P->dangle5[t * 5 + s1i] + (t > 2 ? AUp : 0));
-        }
-        best = warp_min(best);
-        if (lane == 0) F[i] = min(F[i + 1], best);
-        __syncwarp();
-    }
-}
-
 cudaError_t launch_f3(const LocusDesc *loci, int nloci, const unsigned char *codes, const int *C, int *F,
                       const DevParams *P, cudaStream_t st)
 {
     if (nloci == 0) return cudaSuccess;
     const int warps_per_block = 4;
-    static const bool v1 = getenv("MIRFOLD_F3") && !strcmp(getenv("MIRFOLD_F3"), "v1");
-    if (v1) k_f3_v1<<<(nloci + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(loci, nloci, codes, C, F, P);
-    else k_f3<<<(nloci + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(loci, nloci, codes, C, F, P);
+    k_f3<<<(nloci + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(loci, nloci, codes, C, F, P);
     return cudaGetLastError();
 }

@@ -80,6 +80,8 @@ struct Device {
     DevParams *dP = nullptr;
     size_t mem_budget = 0;
     // pooled buffers
+    std::vector<LocusDesc> units_host;   // fill units of the current chunk (pageable: uploaded with a synchronous-staging memcpy)
+    DBuf units;
     DBuf raw, loci, codes, F, C, M, Mp, ring, fillflags, tbcount, tbbase, listoff, startlist, scan_in, scan_out, scan_tmp;
     DBuf slots, tblen, tbstart, tblocus, tbflag, tbenergy, stackscr, fail, ssoff, hitidx;
     DBuf o_start, o_len, o_energy, o_ssoff, o_arena;
@@ -87,7 +89,7 @@ struct Device {
     cudaEvent_t ev[12] = {};
     void release()
     {
-        DBuf *all[] = {&raw, &loci, &codes, &F, &C, &M, &Mp, &ring, &fillflags, &tbcount, &tbbase, &listoff, &startlist, &scan_in,
+        DBuf *all[] = {&units, &raw, &loci, &codes, &F, &C, &M, &Mp, &ring, &fillflags, &tbcount, &tbbase, &listoff, &startlist, &scan_in,
                        &scan_out, &scan_tmp, &slots, &tblen, &tbstart, &tblocus, &tbflag, &tbenergy, &stackscr, &fail,
                        &ssoff, &hitidx, &o_start, &o_len, &o_energy, &o_ssoff, &o_arena};
         for (DBuf *b : all) b->release();
@@ -321,6 +323,69 @@ struct Locus {
     uint64_t cells;
 };
 
+// Band shape of one locus: stride bucket or, for n > MF_TILE_LEN with a span that leaves at least
+// MF_TILE_MIN_STEP owned rows per tile, overlapping tiles for the shared-memory kernels.
+// Returns the band elements (per int32 array) the locus occupies.
+#define MF_TILE_MIN_STEP 64
+unsigned long long shape_locus(LocusDesc &d, int n, int L)
+{
+    d.n = n; d.Ls = std::min(L, n); d.dmax = std::min(d.Ls, n - 1);
+    d.stride = band_stride_for(n);
+    d.tile_last = 0; d.tile_step = 1 << 30; d.tile_rcp = 0;
+    static const bool no_tiles = getenv("MIRFOLD_NO_TILES") != nullptr;   // A/B runs: long loci through k_fill_generic
+    if (n > MF_TILE_LEN && d.dmax >= 4 && MF_TILE_LEN - d.dmax >= MF_TILE_MIN_STEP && !no_tiles) {
+        const int S = MF_TILE_LEN - d.dmax;
+        d.stride = MF_TILE_LEN;
+        d.tile_step = S;
+        d.tile_last = (n - MF_TILE_LEN + S - 1) / S;
+        d.tile_rcp = (unsigned int)((0x100000000ULL + (unsigned long long)S - 1) / (unsigned long long)S);
+        return (unsigned long long)(d.tile_last + 1) * band_elems(MF_TILE_LEN, d.dmax);
+    }
+    return band_elems(d.stride, d.dmax);
+}
+unsigned long long unit_ring_elems(int n, int stride)
+{
+    return (unsigned long long)stride * (n > MF_TILE_LEN ? MF_RING_PER_STRIDE : MF_RING_DML);
+}
+// Fill units of a chunk: one per untiled locus, one per tile otherwise, sorted by descending n
+// so that the stride buckets are contiguous.  Assigns ring offsets; returns ring elements.
+unsigned long long build_fill_units(const LocusDesc *loci, int nl, std::vector<LocusDesc> &units, int bucket_first[5], int &max_n)
+{
+    units.clear();
+    max_n = 0;
+    for (int k = 0; k < nl; k++) {
+        const LocusDesc &d = loci[k];
+        if (d.dmax < 4) continue;   // n < 5 never reaches here; keeps the kernels' assumptions explicit
+        if (d.tile_last == 0) { units.push_back(d); continue; }
+        for (int t = 0; t <= d.tile_last; t++) {
+            LocusDesc u = d;
+            const int a = std::min(t * d.tile_step, d.n - MF_TILE_LEN);
+            u.n = MF_TILE_LEN; u.Ls = std::min(d.Ls, MF_TILE_LEN); u.dmax = d.dmax;
+            u.seq_off = d.seq_off + (unsigned long long)a;
+            u.band_off = d.band_off + (unsigned long long)t * band_elems(MF_TILE_LEN, d.dmax);
+            u.tile_last = 0;
+            units.push_back(u);
+        }
+    }
+    std::stable_sort(units.begin(), units.end(), [](const LocusDesc &a, const LocusDesc &b) { return a.n > b.n; });
+    unsigned long long ring_acc = 0;
+    int k = 0;
+    const int nu = (int)units.size();
+    const int lim[3] = {608, 352, 160};
+    bucket_first[0] = 0;
+    for (int b = 0; b < 3; b++) {
+        while (k < nu && units[k].n > lim[b]) k++;
+        bucket_first[b + 1] = k;
+    }
+    bucket_first[4] = nu;
+    for (auto &u : units) {
+        u.ring_off = ring_acc;
+        ring_acc += unit_ring_elems(u.n, u.stride);
+        max_n = std::max(max_n, u.n);
+    }
+    return ring_acc;
+}
+
 // Runs the full pipeline for `recs` on one device.  If d_raw != nullptr the raw sequences already
 // live on the device (offsets h_off are into that buffer) and no results are downloaded.
 void run_device(Device &D, const char *seqs, const uint64_t *h_off, const std::vector<uint32_t> &recs, int L,
@@ -353,9 +418,10 @@ void run_device(Device &D, const char *seqs, const uint64_t *h_off, const std::v
     struct Chunk { size_t begin, end; };
     std::vector<Chunk> chunks;
     auto locus_bytes = [&](const Locus &l) {
-        const int Ls = std::min(L, l.n), dmax = std::min(Ls, l.n - 1);
-        const int stride = band_stride_for(l.n);
-        return (size_t)band_elems(stride, dmax) * 12 + (size_t)stride * MF_RING_PER_STRIDE * 4 + (size_t)l.n * 16 + 4096;
+        LocusDesc d{};
+        const unsigned long long be = shape_locus(d, l.n, L);
+        return (size_t)be * 12 + (size_t)(d.tile_last + 1) * unit_ring_elems(std::min(l.n, d.tile_last ? MF_TILE_LEN : l.n), d.stride) * 4 +
+               (size_t)(d.tile_last + 2) * sizeof(LocusDesc) + (size_t)l.n * 16 + 4096;
     };
     {
         size_t b = 0, acc = 0;
@@ -383,23 +449,28 @@ void run_device(Device &D, const char *seqs, const uint64_t *h_off, const std::v
         CK(D.h_listoff.ensure(sizeof(unsigned long long) * nl));
         LocusDesc *hl = D.h_loci.as<LocusDesc>();
         unsigned long long *hlo = D.h_listoff.as<unsigned long long>();
-        unsigned long long seq_acc = 0, band_acc = 0, ring_acc = 0, raw_acc = 0, list_acc = 0;
+        unsigned long long seq_acc = 0, band_acc = 0, raw_acc = 0, list_acc = 0;
         int max_n = 0, max_Ls = 0;
         for (int k = 0; k < nl; k++) {
             const Locus &l = loci[cb + k];
             LocusDesc &d = hl[k];
-            d.n = l.n; d.Ls = std::min(L, l.n); d.dmax = std::min(d.Ls, l.n - 1); d.rec = (int)l.rec;
-            d.stride = band_stride_for(l.n);
-            d.seq_off = seq_acc; d.band_off = band_acc; d.ring_off = ring_acc;
+            d = LocusDesc{};
+            const unsigned long long be = shape_locus(d, l.n, L);
+            d.rec = (int)l.rec;
+            d.seq_off = seq_acc; d.band_off = band_acc; d.ring_off = 0;
             d.raw_off = d_raw ? h_off[l.rec] : raw_acc;
             hlo[k] = list_acc;
             seq_acc += (unsigned long long)l.n + 3;
-            band_acc += band_elems(d.stride, d.dmax);
-            ring_acc += (unsigned long long)d.stride * MF_RING_PER_STRIDE;
+            band_acc += be;
             raw_acc += (unsigned long long)l.n;
             list_acc += (unsigned long long)l.n / 2 + 2;
-            max_n = std::max(max_n, l.n); max_Ls = std::max(max_Ls, d.Ls);
+            max_Ls = std::max(max_Ls, d.Ls);
         }
+        std::vector<LocusDesc> &units = D.units_host;
+        int bucket_first[5];
+        const unsigned long long ring_acc = build_fill_units(hl, nl, units, bucket_first, max_n);
+        const int nu = (int)units.size();
+        out.st.fill_units += (uint64_t)nu;
         // ---- upload
         CK(cudaEventRecord(D.ev[0], st));
         const char *raw_dev = d_raw;
@@ -429,24 +500,19 @@ void run_device(Device &D, const char *seqs, const uint64_t *h_off, const std::v
         CK(D.startlist.ensure(list_acc * 4));
         CK(D.fail.ensure(4));
         CK(cudaMemsetAsync(D.fail.p, 0, 4, st));
-        CK(D.fillflags.ensure((size_t)nl * 4));
-        CK(cudaMemsetAsync(D.fillflags.p, 0, (size_t)nl * 4, st));
+        CK(D.fillflags.ensure((size_t)nu * 4 + 4));
+        CK(cudaMemsetAsync(D.fillflags.p, 0, (size_t)nu * 4 + 4, st));
+        CK(D.units.ensure(sizeof(LocusDesc) * (size_t)nu + 64));
+        CK(cudaMemcpyAsync(D.units.p, units.data(), sizeof(LocusDesc) * (size_t)nu, cudaMemcpyHostToDevice, st));
+        out.st.h2d_bytes += sizeof(LocusDesc) * (uint64_t)nu;
         CK(cudaEventRecord(D.ev[1], st));
         // ---- K1..K3
         const LocusDesc *dl = D.loci.as<LocusDesc>();
         CK(launch_prepare(raw_dev, dl, nl, seq_acc, D.codes.as<unsigned char>(), D.F.as<int>(), st));
         CK(cudaEventRecord(D.ev[2], st));
-        FillLaunch fa{dl, nl, max_n, D.codes.as<unsigned char>(), D.C.as<int>(), D.M.as<int>(), D.ring.as<int>(), D.Mp.as<unsigned int>(),
-                      D.dP, {0, 0, 0, 0, 0}, D.fillflags.as<int>(), force_wide ? 1 : 0, env_opts()};
-        {   // loci are sorted by descending n: stride buckets are contiguous
-            int k = 0;
-            const int lim[3] = {608, 352, 160};
-            for (int b = 0; b < 3; b++) {
-                while (k < nl && hl[k].n > lim[b]) k++;
-                fa.bucket_first[b + 1] = k;
-            }
-            fa.bucket_first[4] = nl;
-        }
+        FillLaunch fa{D.units.as<LocusDesc>(), nu, max_n, D.codes.as<unsigned char>(), D.C.as<int>(), D.M.as<int>(), D.ring.as<int>(),
+                      D.Mp.as<unsigned int>(), D.dP, {0, 0, 0, 0, 0}, D.fillflags.as<int>(), force_wide ? 1 : 0, env_opts()};
+        for (int b = 0; b < 5; b++) fa.bucket_first[b] = bucket_first[b];
         CK(launch_fill(fa, st));
         CK(cudaEventRecord(D.ev[3], st));
         CK(launch_f3(dl, nl, D.codes.as<unsigned char>(), D.C.as<int>(), D.F.as<int>(), D.dP, st));
@@ -675,7 +741,7 @@ static void add_stats(mirfold_stats &a, const mirfold_stats &b)
     a.ms_f3 = std::max(a.ms_f3, b.ms_f3); a.ms_trace = std::max(a.ms_trace, b.ms_trace);
     a.ms_d2h = std::max(a.ms_d2h, b.ms_d2h); a.ms_device = std::max(a.ms_device, b.ms_device);
     a.nt += b.nt; a.cells += b.cells; a.tracebacks += b.tracebacks; a.kernel_launches += b.kernel_launches;
-    a.h2d_bytes += b.h2d_bytes; a.d2h_bytes += b.d2h_bytes; a.n_chunks += b.n_chunks;
+    a.h2d_bytes += b.h2d_bytes; a.d2h_bytes += b.d2h_bytes; a.n_chunks += b.n_chunks; a.fill_units += b.fill_units;
 }
 
 static int fold_impl(mirfold_ctx *ctx, const char *seqs, const uint64_t *seq_off, uint32_t nseq, int span_L,
@@ -823,23 +889,26 @@ int mirfold_debug_matrices(mirfold_ctx *ctx, const char *seq, uint32_t n, int sp
     CK(cudaSetDevice(D.id));
     cudaStream_t st = D.stream;
     LocusDesc d{};
-    d.n = (int)n; d.Ls = std::min(span_L, (int)n); d.dmax = std::min(d.Ls, (int)n - 1);
-    d.stride = band_stride_for(d.n);
-    const unsigned long long cells = band_elems(d.stride, d.dmax);
+    const unsigned long long cells = shape_locus(d, (int)n, span_L);
+    std::vector<LocusDesc> units;
+    int bucket_first[5], max_n = 0;
+    const unsigned long long ring_elems = build_fill_units(&d, 1, units, bucket_first, max_n);
+    const int nu = (int)units.size();
     CK(D.raw.ensure(n)); CK(D.loci.ensure(sizeof d)); CK(D.codes.ensure(n + 3)); CK(D.F.ensure((n + 3) * 4));
     CK(D.C.ensure(cells * 4)); CK(D.M.ensure(cells * 4)); CK(D.Mp.ensure(cells * 4));
-    CK(D.ring.ensure((size_t)d.stride * MF_RING_PER_STRIDE * 4));
+    CK(D.ring.ensure((size_t)ring_elems * 4));
+    CK(D.units.ensure(sizeof(LocusDesc) * (size_t)nu + 64));
     CK(cudaMemcpyAsync(D.raw.p, seq, n, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(D.loci.p, &d, sizeof d, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(D.units.p, units.data(), sizeof(LocusDesc) * (size_t)nu, cudaMemcpyHostToDevice, st));
     const LocusDesc *dl = D.loci.as<LocusDesc>();
     CK(launch_prepare(D.raw.as<char>(), dl, 1, n + 3, D.codes.as<unsigned char>(), D.F.as<int>(), st));
-    CK(D.fillflags.ensure(4));
-    CK(cudaMemsetAsync(D.fillflags.p, 0, 4, st));
-    FillLaunch fa{dl, 1, (int)n, D.codes.as<unsigned char>(), D.C.as<int>(), D.M.as<int>(), D.ring.as<int>(), D.Mp.as<unsigned int>(),
-                  D.dP, {0, 0, 0, 0, 1}, D.fillflags.as<int>(), ((flags & MIRFOLD_FLAG_WIDE) || span_L > MF16_MAX_SPAN) ? 1 : 0, env_opts()};
-    fa.bucket_first[1] = d.n > 608 ? 1 : 0;
-    fa.bucket_first[2] = d.n > 352 ? 1 : 0;
-    fa.bucket_first[3] = d.n > 160 ? 1 : 0;
+    CK(D.fillflags.ensure((size_t)nu * 4 + 4));
+    CK(cudaMemsetAsync(D.fillflags.p, 0, (size_t)nu * 4 + 4, st));
+    FillLaunch fa{D.units.as<LocusDesc>(), nu, max_n, D.codes.as<unsigned char>(), D.C.as<int>(), D.M.as<int>(), D.ring.as<int>(),
+                  D.Mp.as<unsigned int>(), D.dP, {0, 0, 0, 0, 0}, D.fillflags.as<int>(),
+                  ((flags & MIRFOLD_FLAG_WIDE) || span_L > MF16_MAX_SPAN) ? 1 : 0, env_opts()};
+    for (int b = 0; b < 5; b++) fa.bucket_first[b] = bucket_first[b];
     CK(launch_fill(fa, st));
     CK(launch_f3(dl, 1, D.codes.as<unsigned char>(), D.C.as<int>(), D.F.as<int>(), D.dP, st));
     std::vector<int> hc(cells), hm(cells), hf(n + 3);
@@ -851,8 +920,15 @@ int mirfold_debug_matrices(mirfold_ctx *ctx, const char *seq, uint32_t n, int sp
     for (size_t k = 0; k < (size_t)(n + 2) * W; k++) c[k] = m[k] = MF_INF;
     for (int dd = 4; dd <= d.dmax; dd++)
         for (int i = 1; i <= (int)n - dd; i++) {
-            c[(size_t)i * W + dd] = hc[band_doff(d.stride, dd) + (i - 1)];
-            m[(size_t)i * W + dd] = hm[band_doff(d.stride, dd) + (i - 1)];
+            // owner tile of row i (same mapping as band_row_base on the device)
+            unsigned long long base = (unsigned long long)(i - 1);
+            if (d.tile_last) {
+                const int t = std::min((i - 1) / d.tile_step, d.tile_last);
+                const int a = std::min(t * d.tile_step, (int)n - MF_TILE_LEN);
+                base = (unsigned long long)t * band_elems(MF_TILE_LEN, d.dmax) + (unsigned long long)(i - 1 - a);
+            }
+            c[(size_t)i * W + dd] = hc[base + band_doff(d.stride, dd)];
+            m[(size_t)i * W + dd] = hm[base + band_doff(d.stride, dd)];
         }
     for (uint32_t k = 0; k < n + 3; k++) f3[k] = hf[k];
     f3[n + 3] = 0;

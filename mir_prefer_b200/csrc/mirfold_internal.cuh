@@ -75,8 +75,27 @@ struct LocusDesc {
     int dmax;    // min(Ls, n-1)
     int rec;     // input record index
     int stride;  // band row stride (elements per diagonal)
-    int pad[3];
+    // Long loci (n > MF_TILE_LEN) are filled as overlapping tiles of MF_TILE_LEN bases by the
+    // shared-memory kernels: tile t covers bases a_t+1 .. a_t+MF_TILE_LEN, a_t = min(t*tile_step,
+    // n-MF_TILE_LEN), tile_step = MF_TILE_LEN - dmax.  Every cell value only depends on the bases
+    // inside [i,j], so a tile's cells are the locus' cells; row i is read from its owner tile
+    // min((i-1)/tile_step, tile_last), which holds all of (i, i+4..i+dmax).  Untiled: tile_last = 0.
+    int tile_last;           // number of tiles - 1
+    int tile_step;           // rows owned per tile
+    unsigned int tile_rcp;   // ceil(2^32 / tile_step): (i-1)/tile_step == __umulhi(i-1, tile_rcp)
 };
+#define MF_TILE_LEN 608
+
+// element offset (relative to the locus' band_off) of row i's owner-tile origin, i.e. of cell
+// (i, i+4); cell (i, i+d) sits (d-4)*stride further.  Any cell (i', j') with i <= i' and
+// j' <= i+dmax may also be addressed relative to row i's tile (columns are local to the tile).
+__device__ __forceinline__ unsigned long long band_row_base(const LocusDesc &L, int i)
+{
+    if (L.tile_last == 0) return (unsigned long long)(i - 1);
+    const int t = min((int)__umulhi((unsigned)(i - 1), L.tile_rcp), L.tile_last);
+    const int a = min(t * L.tile_step, L.n - MF_TILE_LEN);
+    return (unsigned long long)t * ((unsigned long long)(L.dmax - 3) * MF_TILE_LEN) + (unsigned long long)(i - 1 - a);
+}
 
 // offset of diagonal d inside a locus' band (elements)
 __host__ __device__ __forceinline__ unsigned int band_doff(int stride, int d) { return (unsigned int)(d - 4) * (unsigned int)stride; }
@@ -109,7 +128,7 @@ struct FillLaunch {
     int bucket_first[5];  // loci sorted by descending n: [generic | <=608 | <=352 | <=160 | end)
     int *flags;           // per locus: 1 = the 16-bit kernel left its range, redo with the 32-bit kernel
     int force_wide;       // skip the 16-bit kernel (MIRFOLD_FLAG_WIDE)
-    int opts;             // experiment switches (env MIRFOLD_OPTS): bit 0 = no L1 prefetch in the DML strips, bit 2 = previous narrow kernel
+    int opts;             // experiment switches (env MIRFOLD_OPTS): bit 0 = no L1 prefetch in the DML strips, bit 1 = 32-bit DML strips in the narrow kernel, bit 2 = task-queue narrow kernel (fill_narrow.cu)
 };
 cudaError_t launch_prepare(const char *raw, const LocusDesc *loci, int nloci, unsigned long long total_codes,
                            unsigned char *codes, int *F, cudaStream_t st);

@@ -51,6 +51,9 @@ struct Fold {
     const int *__restrict__ M;
     const int *__restrict__ F;
     int n, Ls, NS;
+    // tiled long loci (LocusDesc::tile_*): row i lives in tile min((i-1)/tile_step, tile_last)
+    int tile_last, tile_step, dmax;
+    unsigned int tile_rcp;
     __device__ __forceinline__ int S(int k) const { return cd[k] & 7; }
     __device__ __forceinline__ int S1(int k) const { return cd[k] >> 4; }
     __device__ __forceinline__ int type(int i, int j) const
@@ -63,7 +66,10 @@ struct Fold {
     {
         const int d = j - i;
         if (i < 1 || j > n || d < 4 || d > Ls) return MF_INF;
-        return A[(d - 4) * NS + (i - 1)];
+        if (tile_last == 0) return A[(d - 4) * NS + (i - 1)];
+        const int t = min((int)__umulhi((unsigned)(i - 1), tile_rcp), tile_last);
+        const int a = min(t * tile_step, n - MF_TILE_LEN);
+        return A[(unsigned long long)t * ((unsigned long long)(dmax - 3) * MF_TILE_LEN) + (unsigned)((d - 4) * MF_TILE_LEN + (i - 1 - a))];
     }
     __device__ __forceinline__ int c(int i, int j) const { return band(C, i, j); }
     __device__ __forceinline__ int m(int i, int j) const { return band(M, i, j); }
@@ -131,6 +137,7 @@ __global__ void __launch_bounds__(128) k_traceback(TraceBuffers b)
     Fold f;
     f.P = b.P; f.C = b.C + L.band_off; f.M = b.M + L.band_off; f.F = b.F + L.seq_off;
     f.n = L.n; f.Ls = L.Ls; f.NS = L.stride;
+    f.tile_last = L.tile_last; f.tile_step = L.tile_step; f.dmax = L.dmax; f.tile_rcp = L.tile_rcp;
     const DevParams *__restrict__ P = b.P;
     const int n = L.n;
     const int md = (start == 1) ? L.Ls : L.Ls + 1;   // final backtrack(1, L*) vs backtrack(i+1, L*+1)

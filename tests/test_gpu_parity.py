@@ -128,6 +128,29 @@ def test_long_loci(mf, oracle):
     assert_same(mf, oracle, synth_loci(1003, 2, "long") + synth_loci(12, 4, (1000, 2000)), 300)
 
 
+def test_tiled_long_loci_edges(mf, oracle):
+    """Loci longer than the largest shared-memory bucket are filled as overlapping 608-nt tiles
+    (LocusDesc::tile_*): lengths around every tile-count boundary for L=300 (step 308), and other
+    spans (step 608-L), cell for cell and hit for hit."""
+    lens = [609, 610, 915, 916, 917, 1223, 1224, 1225, 1533, 2500]
+    seqs = [synth_loci(400 + n, 1, (n, n))[0] for n in lens]
+    st = assert_same(mf, oracle, seqs, 300)
+    assert st["fill_units"] == sum((n - 608 + 307) // 308 + 1 for n in lens)
+    assert_same(mf, oracle, seqs[:6], 150)
+    assert_same(mf, oracle, seqs[:4], 500)
+    assert_same(mf, oracle, seqs[:3], 544)     # last tiled span (64 owned rows per tile)
+    assert_same(mf, oracle, seqs[:2], 545)     # first span that uses the generic kernel again
+    for s, L in ((seqs[3], 300), (seqs[5], 150), (seqs[1], 500)):
+        o = oracle.fold(s, L, matrices=True)
+        c, m, f3 = mf.debug_matrices(s, L)
+        assert (o["c"] == c).all()
+        assert (np.minimum(o["m"], 1000000) == np.minimum(m, 1000000)).all()
+        assert (o["f3"][:len(s) + 3] == f3[:len(s) + 3]).all()
+    # a long GC helix leaves the 16-bit range inside some tiles only: those tiles are redone wide
+    s = synth_loci(77, 1, (400, 400))[0] + "GC" * 160 + synth_loci(78, 1, (500, 500))[0]
+    assert_same(mf, oracle, [s], 300)
+
+
 def test_against_reference_binary_live(mf, oracle):
     """When the reference's own RNALfold travelled to this box (oracle/_ref), compare against it."""
     if not oracle.have_rlf():
