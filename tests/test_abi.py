@@ -28,7 +28,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.Hit) == 24
     assert ctypes.sizeof(_lib.DuplexQuery) == 40
     assert ctypes.sizeof(_lib.DuplexVerdict) == 48
-    assert ctypes.sizeof(_lib.Stats) == 7 * 8 + 6 * 8 + 2 * 4
+    assert ctypes.sizeof(_lib.Stats) == 7 * 8 + 6 * 8 + 2 * 4 + 8
     assert _lib.Result.stats.offset == 56
 
 
