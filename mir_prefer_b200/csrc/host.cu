@@ -515,7 +515,10 @@ void run_device(Device &D, const char *seqs, const uint64_t *h_off, const std::v
         for (int b = 0; b < 5; b++) fa.bucket_first[b] = bucket_first[b];
         CK(launch_fill(fa, st));
         CK(cudaEventRecord(D.ev[3], st));
-        CK(launch_f3(dl, nl, D.codes.as<unsigned char>(), D.C.as<int>(), D.F.as<int>(), D.dP, st));
+        int n_long = 0;
+        while (n_long < nl && hl[n_long].n > MF_TILE_LEN) n_long++;   // sorted by descending cells == descending n
+        CK(launch_f3(dl, nl, n_long, max_Ls, D.codes.as<unsigned char>(), D.C.as<int>(), D.F.as<int>(), D.dP, st));
+        out.st.kernel_launches += n_long > 0 && n_long < nl ? 1 : 0;
         CK(cudaEventRecord(D.ev[4], st));
         // ---- K4: plan
         TraceBuffers tb{};
@@ -910,7 +913,7 @@ int mirfold_debug_matrices(mirfold_ctx *ctx, const char *seq, uint32_t n, int sp
                   ((flags & MIRFOLD_FLAG_WIDE) || span_L > MF16_MAX_SPAN) ? 1 : 0, env_opts()};
     for (int b = 0; b < 5; b++) fa.bucket_first[b] = bucket_first[b];
     CK(launch_fill(fa, st));
-    CK(launch_f3(dl, 1, D.codes.as<unsigned char>(), D.C.as<int>(), D.F.as<int>(), D.dP, st));
+    CK(launch_f3(dl, 1, d.n > MF_TILE_LEN ? 1 : 0, d.Ls, D.codes.as<unsigned char>(), D.C.as<int>(), D.F.as<int>(), D.dP, st));
     std::vector<int> hc(cells), hm(cells), hf(n + 3);
     CK(cudaMemcpyAsync(hc.data(), D.C.p, cells * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(hm.data(), D.M.p, cells * 4, cudaMemcpyDeviceToHost, st));

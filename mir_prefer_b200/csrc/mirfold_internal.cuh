@@ -136,8 +136,8 @@ cudaError_t launch_fill(const FillLaunch &a, cudaStream_t st);
 cudaError_t fill_configure_device();
 cudaError_t fill_narrow_configure_device();                                      // fill_narrow.cu
 cudaError_t launch_fill_narrow(const FillLaunch &a, int bucket, cudaStream_t st);    // bucket 0/1/2 = stride 608/352/160
-cudaError_t launch_f3(const LocusDesc *loci, int nloci, const unsigned char *codes, const int *C, int *F,
-                      const DevParams *P, cudaStream_t st);
+cudaError_t launch_f3(const LocusDesc *loci, int nloci, int n_long, int max_Ls, const unsigned char *codes, const int *C, int *F,
+                      const DevParams *P, cudaStream_t st);   // first n_long loci: n > MF_TILE_LEN
 
 struct TraceBuffers {
     const LocusDesc *loci;

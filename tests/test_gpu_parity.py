@@ -140,6 +140,8 @@ def test_tiled_long_loci_edges(mf, oracle):
     assert_same(mf, oracle, seqs[:4], 500)
     assert_same(mf, oracle, seqs[:3], 544)     # last tiled span (64 owned rows per tile)
     assert_same(mf, oracle, seqs[:2], 545)     # first span that uses the generic kernel again
+    for L in (5, 9, 31, 40):                   # f3 CTA kernel windows at tiny spans
+        assert_same(mf, oracle, seqs[:2], L)
     for s, L in ((seqs[3], 300), (seqs[5], 150), (seqs[1], 500)):
         o = oracle.fold(s, L, matrices=True)
         c, m, f3 = mf.debug_matrices(s, L)
