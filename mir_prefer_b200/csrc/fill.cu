@@ -19,6 +19,7 @@
 //   * the 7 table-driven two-loops (stack, 1-nt bulges, 1x1, 1x2, 2x1, 2x2), the hairpin and the
 //     d1 multiloop closing are evaluated lane-per-cell for 32 typed cells at a time.
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include "mirfold_internal.cuh"
@@ -197,32 +198,48 @@ __device__ __forceinline__ void dev_phase_a(const int *Mb, int *rD, StrideT NS, 
 }
 
 
-// phase A on 16-bit row pairs (narrow kernel): Mp[diag][x] holds fML16 of rows x+1 (lo) and x+2 (hi),
-// so a thread owns two rows and one LDG + one VIADDMNMX.S16x2 covers two split terms.  Values are
-// exact while every finite fML of the locus stays above MF16M_GUARD (fML16 INF = 16383: INF+INF and
-// INF+finite stay above MF16M_VALID and never wrap); otherwise the locus is flagged for the 32-bit kernel.
+// phase A on 16-bit row pairs (narrow kernel).  Mp holds fML16 twice per diagonal, as two compact
+// arrays of NS/2 words: E[t] = rows (2t+1 | 2t+2) and O[t] = rows (2t+2 | 2t+3) (lo | hi half).
+// Thread t owns the rows (i, i+1) = (2t+1, 2t+2): the left operand fML(i,i+e) | fML(i+1,i+1+e) is
+// E[t] of diagonal e, the right operand fML(i+e+1, .) | fML(i+e+2, .) is O[t + e/2] (e even) or
+// E[t + (e+1)/2] (e odd), so a warp always reads 32 consecutive words and one LDG + one
+// VIADDMNMX.S16x2 covers two split terms.  Values are exact while every finite fML of the locus
+// stays above MF16M_GUARD (fML16 INF = 16383: INF+INF and INF+finite stay above MF16M_VALID and
+// never wrap); otherwise the locus is flagged for the 32-bit kernel.
+template <class StrideT>
+__device__ __forceinline__ void dev_store_fml16(unsigned int *Mp, StrideT NS, int d, int i, int m, int *sFlag)
+{
+    const int m16 = (m >= MF_INF / 2) ? MF16M_INF : max(m, -32768);
+    if (m < MF16M_GUARD) *sFlag = 1;
+    unsigned short *row = (unsigned short *)(Mp + (d - 4) * NS);
+    // halfword index inside E: i-1; inside O (after NS/2 words = NS halfwords): i-2
+    row[i - 1] = (unsigned short)m16;
+    if (i >= 2) row[NS + i - 2] = (unsigned short)m16;
+}
+
 template <int NT, class StrideT>
 __device__ __forceinline__ void dev_phase_a16(const unsigned int *Mp, int *rD, StrideT NS, int n, int d, int d1,
                                               int tid, bool prefetch)
 {
     const int emax = d1 - 5;  // e ranges 4..emax for the widest diagonal of the strip
     if (emax < 4) return;
+    const int H = NS / 2;
     const int R = n - d, RP = (R + 1) >> 1;
     const int Rpad = (RP + 31) & ~31;
     int nparts = NT / Rpad;
     nparts = max(1, min(nparts, 8));
     const int span = emax - 3;
-    const int per = (span + nparts - 1) / nparts;
+    const int per = ((span + nparts - 1) / nparts + 1) & ~1;      // even: every part starts at an even e
     for (int base = 0; base < Rpad * nparts; base += NT) {
         const int idx = base + tid;
-        const int part = idx / Rpad, i = 2 * (idx - part * Rpad) + 1;   // rows i (lo half) and i+1 (hi half)
+        const int part = idx / Rpad, t = idx - part * Rpad, i = 2 * t + 1;   // rows i (lo half) and i+1 (hi half)
         if (part >= nparts || i > R) continue;
         const int e0 = 4 + part * per, e1 = min(emax, e0 + per - 1);
         if (e0 > e1) continue;
         const int ns = min(d1 - d, n - d - i) + 1;                  // valid strip diagonals for row i
         const int nsh = min(d1 - d, n - d - i - 1) + 1;             // ... and for row i+1 (0 if it has no cell on diagonal d)
-        const unsigned int *pa = Mp + (e0 - 4) * NS + (i - 1);       // fML(i, i+e) | fML(i+1, i+1+e)
-        const unsigned int *pb = Mp + (d - 5 - e0) * NS + (i + e0);  // fML(i+e+1, i+d) | fML(i+e+2, i+1+d)   (+ s*NS for d+s)
+        const unsigned int *pa = Mp + (e0 - 4) * NS + t;                      // E[t] of diagonal e
+        const unsigned int *pb = Mp + (d - 5 - e0) * NS + H + t + (e0 >> 1);  // e even: O[t + e/2] of diagonal d-1-e   (+ s*NS for d+s)
         unsigned int acc[5] = {MF16M_INF2, MF16M_INF2, MF16M_INF2, MF16M_INF2, MF16M_INF2};
         const int emain = min(e1, d - 5);
         int e = e0;
@@ -231,34 +248,27 @@ __device__ __forceinline__ void dev_phase_a16(const unsigned int *Mp, int *rD, S
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
                     dev_prefetch_l1(pa + (8 + k) * NS);
-                    dev_prefetch_l1(pb - (8 + k) * (NS - 1));
+                    dev_prefetch_l1(pb - (8 + k) * NS - (k & 1) * H + 4 + ((k + 1) >> 1));
                 }
             }
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 const unsigned int av = pa[k * NS];
+                // step k: diagonal -k; odd k reads E (H words back) at word t + (e+k+1)/2
+                const int bo = -k * NS - (k & 1) * H + ((k + 1) >> 1);
 #pragma unroll
                 for (int s = 0; s < 5; s++)
-                    if (s < ns) acc[s] = __viaddmin_s16x2(av, pb[s * NS - k * (NS - 1)], acc[s]);
+                    if (s < ns) acc[s] = __viaddmin_s16x2(av, pb[s * NS + bo], acc[s]);
             }
             pa += 4 * NS;
-            pb -= 4 * (NS - 1);
+            pb += -4 * NS + 2;
         }
-        for (; e <= emain; e++) {
-            const unsigned int av = pa[0];
+        for (; e <= e1; e++) {   // remainder and tail: diagonal d+s accepts e <= d+s-5
+            const unsigned int av = Mp[(e - 4) * NS + t];
+            const unsigned int *qb = Mp + (d - 5 - e) * NS + ((e & 1) ? t + ((e + 1) >> 1) : H + t + (e >> 1));
 #pragma unroll
             for (int s = 0; s < 5; s++)
-                if (s < ns) acc[s] = __viaddmin_s16x2(av, pb[s * NS], acc[s]);
-            pa += NS;
-            pb -= (NS - 1);
-        }
-        for (; e <= e1; e++) {   // tail: diagonal d+s accepts e <= d+s-5
-            const unsigned int av = pa[0];
-#pragma unroll
-            for (int s = 1; s < 5; s++)
-                if (s < ns && e <= d + s - 5) acc[s] = __viaddmin_s16x2(av, pb[s * NS], acc[s]);
-            pa += NS;
-            pb -= (NS - 1);
+                if (s < ns && e <= d + s - 5) acc[s] = __viaddmin_s16x2(av, qb[s * NS], acc[s]);
         }
 #pragma unroll
         for (int s = 0; s < 5; s++) {
@@ -564,6 +574,15 @@ __device__ __forceinline__ int dev_fml16(const DevParams *__restrict__ P, const 
     return min(m, rD[(d & (MF_RING_DML - 1)) * NS + i - 1]);
 }
 
+#ifdef MF_TIMELINE   /* per-warp cycle accounting of one CTA (debug builds only: make TIMELINE=1) */
+#define TL_DECL long long tl_acc[6] = {0, 0, 0, 0, 0, 0}; long long tl_t = clock64();
+#define TL_MARK(k) { const long long t_ = clock64(); tl_acc[k] += t_ - tl_t; tl_t = t_; }
+#define TL_DUMP if (blockIdx.x == 3 && lane == 0) printf("TL n=%d warp %2d  dml %8lld  work1 %8lld  bar1 %8lld  work2 %8lld  sync %8lld  other %8lld\n", n, wid, tl_acc[0], tl_acc[1], tl_acc[2], tl_acc[3], tl_acc[4], tl_acc[5]);
+#else
+#define TL_DECL
+#define TL_MARK(k)
+#define TL_DUMP
+#endif
 template <int NS, int NT, int NWM, int MINB>
 __global__ void __launch_bounds__(NT, MINB) k_fill_s16(FillLaunch a)
 {
@@ -627,6 +646,7 @@ __global__ void __launch_bounds__(NT, MINB) k_fill_s16(FillLaunch a)
 
     const unsigned smem_base = (unsigned)__cvta_generic_to_shared(smem_raw);
 
+    TL_DECL
     for (int it = 4; it <= dmax + 1; it++) {
         if (it >= 5 && (it - 5) % 5 == 0 && it - 1 <= dmax) {
             // DML strip [it-1, it+3]
@@ -634,6 +654,7 @@ __global__ void __launch_bounds__(NT, MINB) k_fill_s16(FillLaunch a)
             else dev_phase_a16<NT>(Mp, rD, NS, n, it - 1, min(it + 3, dmax), tid, !(a.opts & 1));
             __syncthreads();
         }
+        TL_MARK(0)
         if (wid < NWC) {
             const int d = it;
             if (d <= dmax) {
@@ -677,7 +698,9 @@ __global__ void __launch_bounds__(NT, MINB) k_fill_s16(FillLaunch a)
                     v = warp_min(v);
                     if (lane == 0) sMy[c] = v;
                 }
+                TL_MARK(1)
                 asm volatile("bar.sync 1, %0;" ::"n"(CT) : "memory");   // c warps only
+                TL_MARK(2)
                 // phase 2: one typed cell per thread -- small loops, hairpin, multiloop closing, stores
                 for (int c = tid; c < ntyped; c += CT) {
                     const int i = (int)(list[c] & 0xffffu) >> 2, j = i + d;
@@ -704,14 +727,10 @@ __global__ void __launch_bounds__(NT, MINB) k_fill_s16(FillLaunch a)
                     const int m = dev_fml16(P, sS, sS1, sPair, sB, RS, Mprev, rD, NS, i, dm, Ls);
                     Mb[(dm - 4) * NS + i - 1] = m;
                     Mcur[i - 1] = m;
-                    // 16-bit copy for the DML strips: lo half of word i-1, hi half of word i-2
-                    const int m16 = (m >= MF_INF / 2) ? MF16M_INF : max(m, -32768);
-                    if (m < MF16M_GUARD) sFlag = 1;
-                    unsigned short *w = (unsigned short *)(Mp + (dm - 4) * NS + i - 1);
-                    w[0] = (unsigned short)m16;
-                    if (i >= 2) w[-1] = (unsigned short)m16;
+                    dev_store_fml16(Mp, NS, dm, i, m, &sFlag);   // 16-bit copies for the DML strips
                 }
             }
+            TL_MARK(1)
             const int dn = it + 1;
             if (mt == 0) sCount[(it + 2) % 3] = 0;
             if (dn <= dmax) {
@@ -735,8 +754,11 @@ __global__ void __launch_bounds__(NT, MINB) k_fill_s16(FillLaunch a)
                     for (int i = mt; i < n; i += MT) rD[((it + s) & (MF_RING_DML - 1)) * NS + i] = MF_INF;
             }
         }
+        TL_MARK(3)
         __syncthreads();
+        TL_MARK(4)
     }
+    TL_DUMP
     if (tid == 0 && sFlag) a.flags[blockIdx.x] = 1;
 }
 
@@ -851,7 +873,6 @@ cudaError_t fill_configure_device()
     if ((e = configure_fill_bucket<608, 512, 2>()) != cudaSuccess) return e;
     if ((e = configure_fill_bucket<352, 384, 3>()) != cudaSuccess) return e;
     if ((e = configure_fill_bucket<160, 256, 4>()) != cudaSuccess) return e;
-    if ((e = fill_narrow_configure_device()) != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_fill_generic<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 }
 
@@ -867,11 +888,8 @@ static cudaError_t launch_fill_bucket(const FillLaunch &a, int first, int count,
     else {
         b.flags = a.flags + first;
         cudaError_t e;
-        if (a.opts & 4) e = launch_fill_narrow(b, NS == 608 ? 0 : NS == 352 ? 1 : 2, st);   // task-queue variant (A/B runs; 8 % slower, r01 s5)
-        else {
-            k_fill_s16<NS, NT, MF16_NWM(NT), MINB><<<count, NT, smem16, st>>>(b);
-            e = cudaGetLastError();
-        }
+        k_fill_s16<NS, NT, MF16_NWM(NT), MINB><<<count, NT, smem16, st>>>(b);
+        e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
     k_fill_smem<NS, NT, MINB><<<count, NT, smem, st>>>(b);   // 32-bit kernel: all loci if forced, else only flagged ones

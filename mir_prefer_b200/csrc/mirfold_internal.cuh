@@ -128,14 +128,12 @@ struct FillLaunch {
     int bucket_first[5];  // loci sorted by descending n: [generic | <=608 | <=352 | <=160 | end)
     int *flags;           // per locus: 1 = the 16-bit kernel left its range, redo with the 32-bit kernel
     int force_wide;       // skip the 16-bit kernel (MIRFOLD_FLAG_WIDE)
-    int opts;             // experiment switches (env MIRFOLD_OPTS): bit 0 = no L1 prefetch in the DML strips, bit 1 = 32-bit DML strips in the narrow kernel, bit 2 = task-queue narrow kernel (fill_narrow.cu)
+    int opts;             // experiment switches (env MIRFOLD_OPTS): bit 0 = no L1 prefetch in the DML strips, bit 1 = 32-bit DML strips in the narrow kernel
 };
 cudaError_t launch_prepare(const char *raw, const LocusDesc *loci, int nloci, unsigned long long total_codes,
                            unsigned char *codes, int *F, cudaStream_t st);
 cudaError_t launch_fill(const FillLaunch &a, cudaStream_t st);
 cudaError_t fill_configure_device();
-cudaError_t fill_narrow_configure_device();                                      // fill_narrow.cu
-cudaError_t launch_fill_narrow(const FillLaunch &a, int bucket, cudaStream_t st);    // bucket 0/1/2 = stride 608/352/160
 cudaError_t launch_f3(const LocusDesc *loci, int nloci, int n_long, int max_Ls, const unsigned char *codes, const int *C, int *F,
                       const DevParams *P, cudaStream_t st);   // first n_long loci: n > MF_TILE_LEN
 
