@@ -286,6 +286,109 @@ __device__ __forceinline__ void dev_phase_a16(const unsigned int *Mp, int *rD, S
     }
 }
 
+// Systolic variant of dev_phase_a16 (the default).  The right operand of thread t at split e and strip
+// diagonal s is the word the next row pair t+1 used two splits earlier for diagonal s-2, so only
+// s = 0, 1 are loaded; s = 2..4 arrive by SHFL.DOWN from lane+1's registers of step e-2 (X*/Y* hold the
+// words of the last even/odd step).  3 LDG + 3 SHFL + 5 VIADDMNMX.S16x2 per step instead of 6 LDG + 5:
+// the strips are bound by L1-miss traffic, not by issue slots.  A warp covers 30 row pairs; lanes 30,
+// 31 are the halo that feeds lanes 28, 29 and are recomputed by the next tile.
+template <int NT, class StrideT>
+__device__ __forceinline__ void dev_phase_a16_sys(const unsigned int *Mp, int *rD, StrideT NS, int n, int d, int d1, int tid)
+{
+    const int emax = d1 - 5;  // e ranges 4..emax for the widest diagonal of the strip
+    if (emax < 4) return;
+    constexpr int NW = NT / 32, TW = 30;
+    const int H = NS / 2;
+    const int R = n - d, RP = (R + 1) >> 1;
+    const int ntiles = (RP + TW - 1) / TW;
+    const int nparts = max(1, min(NW / ntiles, 8));
+    const int span = emax - 3;
+    const int per = ((span + nparts - 1) / nparts + 1) & ~1;      // even: every part starts at an even e
+    const int lane = tid & 31, wid = tid >> 5;
+    for (int unit = wid; unit < ntiles * nparts; unit += NW) {
+        const int part = unit / ntiles, tile = unit - part * ntiles;
+        const int e0 = 4 + part * per, e1 = min(emax, e0 + per - 1);
+        if (e0 > e1) continue;
+        const int t = tile * TW + lane, i = 2 * t + 1;              // rows i (lo half) and i+1 (hi half)
+        const int ns = min(d1 - d, n - d - i) + 1;                  // valid strip diagonals for row i (<= 0: none)
+        const int nsh = min(d1 - d, n - d - i - 1) + 1;             // ... and for row i+1
+        const unsigned int *pa = Mp + (e0 - 4) * NS + t;                      // E[t] of diagonal e
+        const unsigned int *pb = Mp + (d - 5 - e0) * NS + H + t + (e0 >> 1);  // e even: O[t + e/2] of diagonal d-1-e   (+ s*NS for d+s)
+        unsigned int a0 = MF16M_INF2, a1 = MF16M_INF2, a2 = MF16M_INF2, a3 = MF16M_INF2, a4 = MF16M_INF2;
+        const int emain = min(e1, d - 5);
+        unsigned int X0 = 0, X1 = 0, X2 = 0, Y0 = 0, Y1 = 0, Y2 = 0;
+        int e = e0;
+        // every term of the main range is valid for every strip diagonal the row has, and halves / diagonals a
+        // row does not have are simply not stored, so the accumulation is unconditional.
+        // prologue: two steps with all five words loaded
+        if (e <= emain) {
+            const unsigned int av = pa[0];
+            X0 = pb[0]; X1 = pb[NS]; X2 = pb[2 * NS];
+            a0 = __viaddmin_s16x2(av, X0, a0); a1 = __viaddmin_s16x2(av, X1, a1); a2 = __viaddmin_s16x2(av, X2, a2);
+            a3 = __viaddmin_s16x2(av, pb[3 * NS], a3); a4 = __viaddmin_s16x2(av, pb[4 * NS], a4);
+            e++;
+        }
+        if (e <= emain) {
+            const unsigned int av = pa[NS];
+            const unsigned int *q = pb - NS - H + 1;
+            Y0 = q[0]; Y1 = q[NS]; Y2 = q[2 * NS];
+            a0 = __viaddmin_s16x2(av, Y0, a0); a1 = __viaddmin_s16x2(av, Y1, a1); a2 = __viaddmin_s16x2(av, Y2, a2);
+            a3 = __viaddmin_s16x2(av, q[3 * NS], a3); a4 = __viaddmin_s16x2(av, q[4 * NS], a4);
+            e++;
+        }
+        pa += 2 * NS;
+        pb += -2 * NS + 1;
+#define MF_SYS_STEP(V0, V1, V2, AOFF, BOFF)                                                        \
+    {                                                                                              \
+        const unsigned int av = pa[AOFF];                                                          \
+        const unsigned int n0 = pb[BOFF], n1 = pb[(BOFF) + NS];                                    \
+        const unsigned int b2 = __shfl_down_sync(0xffffffffu, V0, 1);                              \
+        const unsigned int b3 = __shfl_down_sync(0xffffffffu, V1, 1);                              \
+        const unsigned int b4 = __shfl_down_sync(0xffffffffu, V2, 1);                              \
+        a0 = __viaddmin_s16x2(av, n0, a0); a1 = __viaddmin_s16x2(av, n1, a1);                      \
+        a2 = __viaddmin_s16x2(av, b2, a2); a3 = __viaddmin_s16x2(av, b3, a3);                      \
+        a4 = __viaddmin_s16x2(av, b4, a4);                                                         \
+        V0 = n0; V1 = n1; V2 = b2;                                                                 \
+    }
+#pragma unroll 2
+        for (; e + 1 <= emain; e += 2) {
+            MF_SYS_STEP(X0, X1, X2, 0, 0)
+            MF_SYS_STEP(Y0, Y1, Y2, NS, -NS - H + 1)
+            pa += 2 * NS;
+            pb += -2 * NS + 1;
+        }
+        if (e <= emain) {
+            MF_SYS_STEP(X0, X1, X2, 0, 0)
+            e++;
+        }
+#undef MF_SYS_STEP
+        for (; e <= e1; e++) {   // tail: diagonal d+s accepts e <= d+s-5 (s >= 1 only), words loaded directly
+            const unsigned int av = Mp[(e - 4) * NS + t];
+            const unsigned int *qb = Mp + (d - 5 - e) * NS + ((e & 1) ? t + ((e + 1) >> 1) : H + t + (e >> 1));
+            if (e <= d + 1 - 5) a1 = __viaddmin_s16x2(av, qb[NS], a1);
+            if (e <= d + 2 - 5) a2 = __viaddmin_s16x2(av, qb[2 * NS], a2);
+            if (e <= d + 3 - 5) a3 = __viaddmin_s16x2(av, qb[3 * NS], a3);
+            a4 = __viaddmin_s16x2(av, qb[4 * NS], a4);
+        }
+        if (lane < TW) {
+            const unsigned int acc[5] = {a0, a1, a2, a3, a4};
+#pragma unroll
+            for (int s = 0; s < 5; s++) {
+                const int lo = (int)(short)(acc[s] & 0xffffu), hi = (int)acc[s] >> 16;
+                int *dst = &rD[((d + s) & (MF_RING_DML - 1)) * NS + (i - 1)];
+                if (s < ns && lo < MF16M_VALID) {
+                    if (nparts == 1) dst[0] = lo;
+                    else atomicMin(dst, lo);
+                }
+                if (s < nsh && hi < MF16M_VALID) {
+                    if (nparts == 1) dst[1] = hi;
+                    else atomicMin(dst + 1, hi);
+                }
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------ K2 (shared-memory rings)
 // Ring geometry: 33 slots hold Cm of diagonals d-32..d, slot 33 is all-INF.  Rows are RS = NS+32
 // words; diagonal d' is stored rotated by sk(d') = (11*d') & 31 words, which makes the bank of
@@ -651,7 +754,8 @@ __global__ void __launch_bounds__(NT, MINB) k_fill_s16(FillLaunch a)
         if (it >= 5 && (it - 5) % 5 == 0 && it - 1 <= dmax) {
             // DML strip [it-1, it+3]
             if (a.opts & 2) dev_phase_a<NT>(Mb, rD, NS, n, it - 1, min(it + 3, dmax), tid, !(a.opts & 1));
-            else dev_phase_a16<NT>(Mp, rD, NS, n, it - 1, min(it + 3, dmax), tid, !(a.opts & 1));
+            else if (a.opts & 4) dev_phase_a16<NT>(Mp, rD, NS, n, it - 1, min(it + 3, dmax), tid, !(a.opts & 1));
+            else dev_phase_a16_sys<NT>(Mp, rD, NS, n, it - 1, min(it + 3, dmax), tid);
             __syncthreads();
         }
         TL_MARK(0)
