@@ -4,7 +4,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmirfold.so")
+# MIRFOLD_LIB_PATH: load another build of the same library (kernel A/B experiments); never a fallback
+LIB_PATH = os.environ.get("MIRFOLD_LIB_PATH") or os.path.join(_HERE, "libmirfold.so")
 
 
 class MirfoldError(RuntimeError):

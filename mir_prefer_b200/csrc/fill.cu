@@ -350,7 +350,12 @@ __device__ __forceinline__ void dev_phase_a16_sys(const unsigned int *Mp, int *r
         a4 = __viaddmin_s16x2(av, b4, a4);                                                         \
         V0 = n0; V1 = n1; V2 = b2;                                                                 \
     }
-#pragma unroll 2
+#ifndef MF_SYS_UNROLL
+#define MF_SYS_UNROLL 2
+#endif
+#define MF_PRAGMA_(x) _Pragma(#x)
+#define MF_UNROLL_(n) MF_PRAGMA_(unroll n)
+        MF_UNROLL_(MF_SYS_UNROLL)
         for (; e + 1 <= emain; e += 2) {
             MF_SYS_STEP(X0, X1, X2, 0, 0)
             MF_SYS_STEP(Y0, Y1, Y2, NS, -NS - H + 1)
@@ -766,6 +771,16 @@ __global__ void __launch_bounds__(NT, MINB) k_fill_s16(FillLaunch a)
                 const int ntyped = sCount[d % 3];
                 const unsigned int *list = sList + par * NS;
                 const int K = min(30, d - 6);
+#ifndef MF_NO_TAIL_PREFETCH
+                // phase 2 of this thread's cell reads DML(d-2..d-4) from the global ring: start pulling those
+                // lines into L1 now, the interior-loop phase hides the L2 latency
+                if (tid < ntyped && d >= 8) {
+                    const int i = (int)(list[tid] & 0xffffu) >> 2;
+                    dev_prefetch_l1(&rD[((d - 2) & (MF_RING_DML - 1)) * NS + i]);
+                    dev_prefetch_l1(&rD[((d - 3) & (MF_RING_DML - 1)) * NS + i]);
+                    dev_prefetch_l1(&rD[((d - 4) & (MF_RING_DML - 1)) * NS + i + 1]);
+                }
+#endif
                 // per-lane word-term addresses (bytes, shared window) and packed constants
                 unsigned off[MF16_NQ], cst[MF16_NQ], mk[MF16_NMK];
 #pragma unroll
