@@ -258,6 +258,7 @@ def run_ours(args, rank, world, local_rank):
         r = mf.fold_packed(host_buf, off, SPAN)
         h2d, d2h = r.stats["h2d_bytes"], r.stats["d2h_bytes"]
         nhits = r.nhits
+        e2e_split = {k: r.stats[k] for k in ("ms_total", "ms_h2d", "ms_device", "ms_d2h")}
         r.close()
     barrier()
     t_e2e = time.perf_counter() - t0
@@ -295,7 +296,7 @@ def run_ours(args, rank, world, local_rank):
                                    % (band_bytes / 1e9), "tracebacks_per_step": int(tracebacks)},
             "dp_cells_per_s": cells_all * args.steps / t_dev,
             "e2e": {"value": nt_all * args.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * t_e2e / args.steps, "hits_per_step": int(nhits)},
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * t_e2e / args.steps, "hits_per_step": int(nhits), "last_step_split": e2e_split},
             "gpu_launches": int(launches),
             "stage_ms": dict(stage, chunks=int(n_chunks)),
             "clocks": clocks,

@@ -78,7 +78,9 @@ typedef struct mirfold_result {
     uint32_t nseq;
     uint32_t reserved;
     uint64_t nhits;
-    const uint64_t *hit_begin;   /* nseq+1 entries: hits of record r are [hit_begin[r], hit_begin[r+1]) */
+    const uint64_t *hit_begin;   /* nseq entries: hits of record r are hits[hit_begin[r] .. hit_begin[r]+hit_count[r]) */
+    const uint32_t *hit_count;   /* nseq entries.  Runs of different records are disjoint but NOT ordered by r: the
+                                    table is left in the order the devices produced it (no per-hit host pass)    */
     const mirfold_hit *hits;     /* nhits entries                                                      */
     const char *ss_arena;        /* dot-bracket strings, NUL-terminated                                */
     uint64_t ss_bytes;

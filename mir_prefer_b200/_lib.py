@@ -35,7 +35,7 @@ class Stats(C.Structure):
 
 class Result(C.Structure):
     _fields_ = [("nseq", C.c_uint32), ("reserved", C.c_uint32), ("nhits", C.c_uint64),
-                ("hit_begin", C.POINTER(C.c_uint64)), ("hits", C.POINTER(Hit)), ("ss_arena", C.c_void_p),
+                ("hit_begin", C.POINTER(C.c_uint64)), ("hit_count", C.POINTER(C.c_uint32)), ("hits", C.POINTER(Hit)), ("ss_arena", C.c_void_p),
                 ("ss_bytes", C.c_uint64), ("total_mfe_dcal", C.POINTER(C.c_int32)), ("stats", Stats)]
 
 

@@ -66,7 +66,8 @@ struct Partial {  // what one device produced for its share of the records
     std::vector<uint64_t> rec_hit_begin;   // per handled record: first hit in `hits`
     std::vector<uint32_t> rec_hit_count;
     std::vector<int32_t> rec_total;
-    std::vector<mirfold_hit> hits;         // ss_off relative to arena
+    HBuf hits;                             // pinned mirfold_hit[nhits], locus order; ss_off relative to arena
+    uint64_t nhits = 0;
     HBuf arena;                            // pinned
     uint64_t arena_bytes = 0;
     mirfold_stats st{};
@@ -84,14 +85,14 @@ struct Device {
     DBuf units;
     DBuf raw, loci, codes, F, C, M, Mp, ring, fillflags, tbcount, tbbase, listoff, startlist, scan_in, scan_out, scan_tmp;
     DBuf slots, tblen, tbstart, tblocus, tbflag, tbenergy, stackscr, fail, ssoff, hitidx;
-    DBuf o_start, o_len, o_energy, o_ssoff, o_arena;
+    DBuf o_hits, o_arena;
     HBuf h_raw, h_loci, h_listoff, h_small, h_out;
     cudaEvent_t ev[12] = {};
     void release()
     {
         DBuf *all[] = {&units, &raw, &loci, &codes, &F, &C, &M, &Mp, &ring, &fillflags, &tbcount, &tbbase, &listoff, &startlist, &scan_in,
                        &scan_out, &scan_tmp, &slots, &tblen, &tbstart, &tblocus, &tbflag, &tbenergy, &stackscr, &fail,
-                       &ssoff, &hitidx, &o_start, &o_len, &o_energy, &o_ssoff, &o_arena};
+                       &ssoff, &hitidx, &o_hits, &o_arena};
         for (DBuf *b : all) b->release();
         HBuf *hall[] = {&h_raw, &h_loci, &h_listoff, &h_small, &h_out};
         for (HBuf *b : hall) b->release();
@@ -109,6 +110,7 @@ struct mirfold_ctx {
     std::vector<Device> devs;
     std::string last_error;
     std::vector<HBuf> arena_pool;  // pinned arenas returned by mirfold_free_result
+    std::vector<HBuf> hits_pool;   // pinned hit tables returned by mirfold_free_result
     std::mutex pool_mu;
 };
 
@@ -118,7 +120,9 @@ struct ResultOwner {  // lives right behind the public struct
     mirfold_result pub;
     mirfold_ctx *ctx;
     std::vector<uint64_t> hit_begin;
-    std::vector<mirfold_hit> hits;
+    std::vector<uint32_t> hit_count;
+    HBuf hits;                 // single-device fast path: pinned hit table moved from the Partial
+    std::vector<mirfold_hit> hits_v;   // multi-device path: concatenated
     std::vector<int32_t> totals;
     HBuf arena;               // single-device fast path: pinned arena moved from the Partial
     std::vector<char> arena_v;  // multi-device path: concatenated
@@ -249,6 +253,20 @@ void build_params(DevParams &P)
         for (int v = 0; v <= 30 - u; v++) { P.uv[m][0] = (unsigned char)u; P.uv[m][1] = (unsigned char)v; m++; }
     build_s16_schedule(P);
 }
+
+// host-side phase log (MIRFOLD_HOST_TIMING=1): where the wall time outside the kernels goes
+struct HostTimer {
+    std::chrono::steady_clock::time_point t;
+    bool on;
+    HostTimer() : t(std::chrono::steady_clock::now()) { static const bool e = getenv("MIRFOLD_HOST_TIMING") != nullptr; on = e; }
+    void mark(const char *what)
+    {
+        if (!on) return;
+        const auto n = std::chrono::steady_clock::now();
+        fprintf(stderr, "[mirfold host] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
+        t = n;
+    }
+};
 
 int env_opts()
 {
@@ -411,9 +429,11 @@ void run_device(Device &D, const char *seqs, const uint64_t *h_off, const std::v
     // largest first: the hardware CTA scheduler then behaves like LPT list scheduling
     std::stable_sort(loci.begin(), loci.end(), [](const Locus &a, const Locus &b) { return a.cells > b.cells; });
 
-    out.recs.clear(); out.rec_hit_begin.clear(); out.rec_hit_count.clear(); out.rec_total.clear(); out.hits.clear();
+    out.recs.clear(); out.rec_hit_begin.clear(); out.rec_hit_count.clear(); out.rec_total.clear(); out.nhits = 0;
     out.arena_bytes = 0;
 
+    HostTimer ht;
+    ht.mark("sort loci");
     // ---- chunking by device memory budget
     struct Chunk { size_t begin, end; };
     std::vector<Chunk> chunks;
@@ -437,7 +457,6 @@ void run_device(Device &D, const char *seqs, const uint64_t *h_off, const std::v
     struct ChunkOut {  // device-resident results of a chunk, downloaded at the end
         uint64_t nhits, arena_bytes;
     };
-    std::vector<mirfold_hit> &hits = out.hits;
     // pass 1 over chunks computes everything and downloads the small per-hit arrays + arena
     // into the pinned arena (grown as needed; chunks are few).
     std::vector<char> arena_tmp;  // only used when more than one chunk
@@ -471,6 +490,7 @@ void run_device(Device &D, const char *seqs, const uint64_t *h_off, const std::v
         const unsigned long long ring_acc = build_fill_units(hl, nl, units, bucket_first, max_n);
         const int nu = (int)units.size();
         out.st.fill_units += (uint64_t)nu;
+        ht.mark("descriptors + fill units");
         // ---- upload
         CK(cudaEventRecord(D.ev[0], st));
         const char *raw_dev = d_raw;
@@ -506,6 +526,7 @@ void run_device(Device &D, const char *seqs, const uint64_t *h_off, const std::v
         CK(cudaMemcpyAsync(D.units.p, units.data(), sizeof(LocusDesc) * (size_t)nu, cudaMemcpyHostToDevice, st));
         out.st.h2d_bytes += sizeof(LocusDesc) * (uint64_t)nu;
         CK(cudaEventRecord(D.ev[1], st));
+        ht.mark("stage raw + enqueue uploads");
         // ---- K1..K3
         const LocusDesc *dl = D.loci.as<LocusDesc>();
         CK(launch_prepare(raw_dev, dl, nl, seq_acc, D.codes.as<unsigned char>(), D.F.as<int>(), st));
@@ -538,6 +559,7 @@ void run_device(Device &D, const char *seqs, const uint64_t *h_off, const std::v
         const unsigned long long ntb = hs[0];
         out.st.tracebacks += ntb;
         out.st.kernel_launches += 6;
+        ht.mark("K1-K3 enqueue + plan sync");
         // ---- traceback
         tb.ntb = ntb;
         tb.slot_stride = (max_Ls + 4 + 3) & ~3;
@@ -571,30 +593,30 @@ void run_device(Device &D, const char *seqs, const uint64_t *h_off, const std::v
         CK(cudaStreamSynchronize(st));
         if (*(int *)&hs[3]) { out.err = MIRFOLD_ERR_BACKTRACK; out.errmsg = "traceback found no decomposition"; return; }
         if (ntb) { abytes = hs[1]; nhits = hs[2]; }
-        CK(D.o_start.ensure(nhits * 4 + 16)); CK(D.o_len.ensure(nhits * 4 + 16)); CK(D.o_energy.ensure(nhits * 4 + 16));
-        CK(D.o_ssoff.ensure(nhits * 8 + 16)); CK(D.o_arena.ensure(abytes + 16));
+        CK(D.o_hits.ensure(nhits * sizeof(mirfold_hit) + 16)); CK(D.o_arena.ensure(abytes + 16));
         CK(launch_pack(tb, D.ssoff.as<unsigned long long>(), D.hitidx.as<unsigned long long>(), D.o_arena.as<char>(),
-                       D.o_start.as<int>(), D.o_len.as<int>(), D.o_energy.as<int>(), D.o_ssoff.as<unsigned long long>(), st));
+                       D.o_hits.as<mirfold_hit>(), out.arena_bytes, st));
         out.st.kernel_launches += 1;
         CK(cudaEventRecord(D.ev[5], st));
+        ht.mark("traceback..pack (sync inside)");
         // ---- download
-        const size_t small_bytes = (size_t)nhits * (4 + 4 + 4 + 8) + (size_t)(nl + 1) * 8 * 2 + seq_acc * 0 + 64;
         if (download) {
             // per-locus first-hit index = hitidx[tb_base[l]] -> gather on host from two small arrays
-            CK(D.h_out.ensure(small_bytes + (size_t)ntb * 0 + (size_t)nl * 4 + 64));
-            char *ho = D.h_out.as<char>();
-            int *h_start = (int *)ho;
-            int *h_len = h_start + nhits;
-            int *h_energy = h_len + nhits;
-            unsigned long long *h_ssoff = (unsigned long long *)(((uintptr_t)(h_energy + nhits) + 7) & ~(uintptr_t)7);
-            unsigned long long *h_tbbase = h_ssoff + nhits;
+            CK(D.h_out.ensure((size_t)(nl + 1) * 8 + (size_t)nl * 4 + 64));
+            unsigned long long *h_tbbase = D.h_out.as<unsigned long long>();
             int *h_total = (int *)(h_tbbase + nl + 1);
-            if (nhits) {
-                CK(cudaMemcpyAsync(h_start, D.o_start.p, nhits * 4, cudaMemcpyDeviceToHost, st));
-                CK(cudaMemcpyAsync(h_len, D.o_len.p, nhits * 4, cudaMemcpyDeviceToHost, st));
-                CK(cudaMemcpyAsync(h_energy, D.o_energy.p, nhits * 4, cudaMemcpyDeviceToHost, st));
-                CK(cudaMemcpyAsync(h_ssoff, D.o_ssoff.p, nhits * 8, cudaMemcpyDeviceToHost, st));
+            // hit table: the device wrote finished mirfold_hit records (ss_off already includes this chunk's
+            // arena base); they land in the pinned table the result will own -- no per-hit host work
+            const uint64_t hbase = out.nhits;
+            if (out.hits.cap < (hbase + nhits) * sizeof(mirfold_hit) + 16) {
+                HBuf bigger;
+                CK(bigger.ensure((hbase + nhits) * sizeof(mirfold_hit) * (hbase ? 2 : 1) + 16));
+                if (hbase) memcpy(bigger.p, out.hits.p, hbase * sizeof(mirfold_hit));
+                out.hits.release();
+                out.hits = bigger;
             }
+            if (nhits)
+                CK(cudaMemcpyAsync(out.hits.as<mirfold_hit>() + hbase, D.o_hits.p, nhits * sizeof(mirfold_hit), cudaMemcpyDeviceToHost, st));
             // hit index at each locus boundary: hitidx[tb_base[l]] (device gather -> reuse scan_in)
             {
                 // gather kernel inline via thrust-free lambda: small kernel below
@@ -629,14 +651,9 @@ void run_device(Device &D, const char *seqs, const uint64_t *h_off, const std::v
             if (abytes) CK(cudaMemcpyAsync(out.arena.as<char>() + abase, D.o_arena.p, abytes, cudaMemcpyDeviceToHost, st));
             CK(cudaEventRecord(D.ev[6], st));
             CK(cudaStreamSynchronize(st));
-            out.st.d2h_bytes += nhits * 20 + (uint64_t)(nl + 1) * 8 + (uint64_t)nl * 4 + abytes + 32;
-            const uint64_t hbase = hits.size();
-            hits.resize(hbase + nhits);
-            for (uint64_t h = 0; h < nhits; h++) {
-                mirfold_hit &x = hits[hbase + h];
-                x.start = h_start[h]; x.len = h_len[h]; x.mfe_dcal = h_energy[h]; x.reserved = 0;
-                x.ss_off = abase + h_ssoff[h];
-            }
+            out.st.d2h_bytes += nhits * sizeof(mirfold_hit) + (uint64_t)(nl + 1) * 8 + (uint64_t)nl * 4 + abytes + 32;
+            ht.mark("download + sync");
+            out.nhits = hbase + nhits;
             for (int k = 0; k < nl; k++) {
                 out.recs.push_back(loci[cb + k].rec);
                 out.rec_hit_begin.push_back(hbase + h_tbbase[k]);
@@ -644,6 +661,7 @@ void run_device(Device &D, const char *seqs, const uint64_t *h_off, const std::v
                 out.rec_total.push_back(h_total[k]);
             }
             out.arena_bytes = abase + abytes;
+            ht.mark("hit records");
         } else {
             CK(cudaEventRecord(D.ev[6], st));
             CK(cudaStreamSynchronize(st));
@@ -735,6 +753,7 @@ void mirfold_close(mirfold_ctx *ctx)
     if (!ctx) return;
     for (auto &D : ctx->devs) { cudaSetDevice(D.id); D.release(); }
     for (auto &b : ctx->arena_pool) b.release();
+    for (auto &b : ctx->hits_pool) b.release();
     delete ctx;
 }
 
@@ -778,6 +797,7 @@ static int fold_impl(mirfold_ctx *ctx, const char *seqs, const uint64_t *seq_off
     {
         std::lock_guard<std::mutex> lk(ctx->pool_mu);
         for (int g = 0; g < G && !ctx->arena_pool.empty(); g++) { parts[g].arena = ctx->arena_pool.back(); ctx->arena_pool.pop_back(); }
+        for (int g = 0; g < G && !ctx->hits_pool.empty(); g++) { parts[g].hits = ctx->hits_pool.back(); ctx->hits_pool.pop_back(); }
     }
     if (G == 1) run_device(ctx->devs[0], seqs, seq_off, shard[0], span_L, d_raw, download, (cudaStream_t)stream, force_wide, parts[0]);
     else {
@@ -789,36 +809,47 @@ static int fold_impl(mirfold_ctx *ctx, const char *seqs, const uint64_t *seq_off
     for (int g = 0; g < G; g++)
         if (parts[g].err != MIRFOLD_OK) {
             ctx->last_error = parts[g].errmsg;
-            for (auto &p : parts) p.arena.release();
+            for (auto &p : parts) { p.arena.release(); p.hits.release(); }
             return parts[g].err;
         }
+    HostTimer ht;
     // ---- gather in input order
     ResultOwner *R = new ResultOwner();
     R->ctx = ctx;
     R->hit_begin.assign((size_t)nseq + 1, 0);
+    R->hit_count.assign((size_t)nseq + 1, 0);
     R->totals.assign(nseq, 0);
     mirfold_stats st{};
     uint64_t nhits = 0;
     if (download) {
-        std::vector<uint32_t> cnt(nseq, 0);
-        std::vector<uint64_t> arena_base(G, 0);
+        // Hits stay in the order the devices produced them (locus order inside a device, devices
+        // concatenated); a record finds its run through hit_begin / hit_count.
+        std::vector<uint64_t> arena_base(G, 0), hit_base(G, 0);
         uint64_t abytes = 0;
-        for (int g = 0; g < G; g++) { arena_base[g] = abytes; abytes += parts[g].arena_bytes; }
-        for (int g = 0; g < G; g++)
-            for (size_t k = 0; k < parts[g].recs.size(); k++) {
-                cnt[parts[g].recs[k]] = parts[g].rec_hit_count[k];
-                R->totals[parts[g].recs[k]] = parts[g].rec_total[k];
-            }
-        for (uint32_t r = 0; r < nseq; r++) R->hit_begin[r + 1] = R->hit_begin[r] + cnt[r];
-        nhits = R->hit_begin[nseq];
-        R->hits.resize(nhits);
+        for (int g = 0; g < G; g++) { arena_base[g] = abytes; abytes += parts[g].arena_bytes; hit_base[g] = nhits; nhits += parts[g].nhits; }
         for (int g = 0; g < G; g++)
             for (size_t k = 0; k < parts[g].recs.size(); k++) {
                 const uint32_t r = parts[g].recs[k];
-                const mirfold_hit *src = parts[g].hits.data() + parts[g].rec_hit_begin[k];
-                mirfold_hit *dst = R->hits.data() + R->hit_begin[r];
-                for (uint32_t h = 0; h < parts[g].rec_hit_count[k]; h++) { dst[h] = src[h]; dst[h].ss_off += arena_base[g]; }
+                R->hit_begin[r] = hit_base[g] + parts[g].rec_hit_begin[k];
+                R->hit_count[r] = parts[g].rec_hit_count[k];
+                R->totals[r] = parts[g].rec_total[k];
             }
+        if (G == 1) {
+            R->hits = parts[0].hits;    // pinned table moves into the result
+            parts[0].hits = HBuf();
+            R->pub.hits = R->hits.as<mirfold_hit>();
+        } else {
+            R->hits_v.resize(nhits);
+            for (int g = 0; g < G; g++) {
+                const mirfold_hit *src = parts[g].hits.as<mirfold_hit>();
+                mirfold_hit *dst = R->hits_v.data() + hit_base[g];
+                for (uint64_t h = 0; h < parts[g].nhits; h++) { dst[h] = src[h]; dst[h].ss_off += arena_base[g]; }
+                std::lock_guard<std::mutex> lk(ctx->pool_mu);
+                ctx->hits_pool.push_back(parts[g].hits);
+                parts[g].hits = HBuf();
+            }
+            R->pub.hits = R->hits_v.data();
+        }
         if (G == 1) {
             R->arena = parts[0].arena;  // pinned buffer moves into the result
             parts[0].arena = HBuf();
@@ -836,16 +867,22 @@ static int fold_impl(mirfold_ctx *ctx, const char *seqs, const uint64_t *seq_off
         R->pub.ss_bytes = abytes;
     } else {
         for (int g = 0; g < G; g++) { for (uint64_t v : parts[g].rec_hit_begin) nhits += v; R->pub.ss_bytes += parts[g].arena_bytes; }
-        for (auto &p : parts) if (p.arena.p) { std::lock_guard<std::mutex> lk(ctx->pool_mu); ctx->arena_pool.push_back(p.arena); p.arena = HBuf(); }
+        for (auto &p : parts) {
+            std::lock_guard<std::mutex> lk(ctx->pool_mu);
+            if (p.arena.p) { ctx->arena_pool.push_back(p.arena); p.arena = HBuf(); }
+            if (p.hits.p) { ctx->hits_pool.push_back(p.hits); p.hits = HBuf(); }
+        }
         R->pub.ss_arena = nullptr;
+        R->pub.hits = nullptr;
     }
+    ht.mark("gather in input order");
     for (int g = 0; g < G; g++) add_stats(st, parts[g].st);
     st.n_devices = G;
     st.ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     R->pub.nseq = nseq;
     R->pub.nhits = nhits;
     R->pub.hit_begin = R->hit_begin.data();
-    R->pub.hits = R->hits.data();
+    R->pub.hit_count = R->hit_count.data();
     R->pub.total_mfe_dcal = R->totals.data();
     R->pub.stats = st;
     *out = &R->pub;
@@ -874,7 +911,12 @@ void mirfold_free_result(mirfold_result *res)
         std::lock_guard<std::mutex> lk(R->ctx->pool_mu);
         if (R->ctx->arena_pool.size() < 4) { R->ctx->arena_pool.push_back(R->arena); R->arena = HBuf(); }
     }
+    if (R->hits.p && R->ctx) {
+        std::lock_guard<std::mutex> lk(R->ctx->pool_mu);
+        if (R->ctx->hits_pool.size() < 4) { R->ctx->hits_pool.push_back(R->hits); R->hits = HBuf(); }
+    }
     R->arena.release();
+    R->hits.release();
     delete R;
 }
 

@@ -165,9 +165,9 @@ struct TraceBuffers {
 cudaError_t launch_plan(const TraceBuffers &b, cudaStream_t st);
 cudaError_t launch_traceback(const TraceBuffers &b, cudaStream_t st);
 cudaError_t launch_emit(const TraceBuffers &b, cudaStream_t st);
+struct mirfold_hit;
 cudaError_t launch_pack(const TraceBuffers &b, const unsigned long long *ss_off, const unsigned long long *hit_idx,
-                        char *arena, int *out_start, int *out_len, int *out_energy, unsigned long long *out_ssoff,
-                        cudaStream_t st);
+                        char *arena, mirfold_hit *out_hits, unsigned long long arena_base, cudaStream_t st);
 cudaError_t run_int_peak(cudaStream_t st, int sm_count, double *addmin, double *dpx);
 struct mirfold_duplex_query;
 struct mirfold_duplex_verdict;

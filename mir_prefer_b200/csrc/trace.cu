@@ -9,9 +9,13 @@
 //   k_emit      : the shifted-strncmp containment test between consecutive tracebacks decides
 //                 which structures RNALfold would have printed; energy = f3[start]-f3[start+len]
 //   k_pack      : compacts printed structures into the result arena (offsets from a device scan)
+#include "../../include/mirfold.h"
 #include "mirfold_internal.cuh"
 
 #define FULL 0xffffffffu
+#ifndef TB_UNR
+#define TB_UNR 1   /* 32-candidate chunks evaluated per round of a first-match scan */
+#endif
 
 // ------------------------------------------------------------------------------------ plan
 __global__ void k_plan(TraceBuffers b)
@@ -44,6 +48,14 @@ cudaError_t launch_plan(const TraceBuffers &b, cudaStream_t st)
 }
 
 // ------------------------------------------------------------------------------------ traceback
+// band offset of cell (i, i+d) of a tiled long locus (LocusDesc::tile_*, see band_row_base)
+__device__ __noinline__ unsigned long long tb_tiled_off(int i, int d, unsigned int tile_rcp, int tile_last, int tile_step, int n, int dmax)
+{
+    const int t = min((int)__umulhi((unsigned)(i - 1), tile_rcp), tile_last);
+    const int a = min(t * tile_step, n - MF_TILE_LEN);
+    return (unsigned long long)t * ((unsigned long long)(dmax - 3) * MF_TILE_LEN) + (unsigned)((d - 4) * MF_TILE_LEN + (i - 1 - a));
+}
+
 struct Fold {
     const DevParams *__restrict__ P;
     const unsigned char *__restrict__ cd;  // codes, 1-based
@@ -66,10 +78,9 @@ struct Fold {
     {
         const int d = j - i;
         if (i < 1 || j > n || d < 4 || d > Ls) return MF_INF;
-        if (tile_last == 0) return A[(d - 4) * NS + (i - 1)];
-        const int t = min((int)__umulhi((unsigned)(i - 1), tile_rcp), tile_last);
-        const int a = min(t * tile_step, n - MF_TILE_LEN);
-        return A[(unsigned long long)t * ((unsigned long long)(dmax - 3) * MF_TILE_LEN) + (unsigned)((d - 4) * MF_TILE_LEN + (i - 1 - a))];
+        unsigned long long off = (unsigned)((d - 4) * NS + (i - 1));
+        if (tile_last) off = tb_tiled_off(i, d, tile_rcp, tile_last, tile_step, n, dmax);   // warp-uniform branch, out of line: not if-converted into the common path
+        return A[off];
     }
     __device__ __forceinline__ int c(int i, int j) const { return band(C, i, j); }
     __device__ __forceinline__ int m(int i, int j) const { return band(M, i, j); }
@@ -119,7 +130,10 @@ __device__ int tb_hairpin(const Fold &f, int i, int j, int t)
 }
 
 // one warp per traceback
-__global__ void __launch_bounds__(128) k_traceback(TraceBuffers b)
+#ifndef TB_MINB
+#define TB_MINB 10
+#endif
+__global__ void __launch_bounds__(128, TB_MINB) k_traceback(TraceBuffers b)
 {
     const unsigned long long g = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -181,30 +195,38 @@ __global__ void __launch_bounds__(128) k_traceback(TraceBuffers b)
             const int fij = f.f(i);
             if (fij == f.f(i + 1)) { PUSH(i + 1, j, 0); continue; }
             int traced = 0, jj = 0, kk = 0;
-            for (int kb = i + 4; kb <= j; kb += 32) {
-                const int k = kb + lane;
-                int tr = 0, myjj = k + 1;
-                if (k <= j) {
-                    int t = f.type(i + 1, k);
-                    if (t) {
-                        const int cc = f.c(i + 1, k) + P->dangle5[t * 5 + f.S1(i)] + f.AU(t);
-                        if (fij == cc + f.f(k + 1)) tr = i + 1;
-                        if (k < n && fij == f.f(k + 2) + cc + P->dangle3[t * 5 + f.S1(k + 1)]) { tr = i + 1; myjj = k + 2; }
-                    }
-                    t = f.type(i, k);
-                    if (t) {
-                        const int cc = f.c(i, k) + f.AU(t);
-                        if (fij == cc + f.f(k + 1)) tr = i;
-                        if (k < n && fij == f.f(k + 2) + cc + P->dangle3[t * 5 + f.S1(k + 1)]) { tr = i; myjj = k + 2; }
+            // candidates k = i+4 .. j in reference order; TB_UNR chunks of 32 per round so that the band / f3
+            // loads of a round are all in flight together (the scan is latency-bound, not issue-bound)
+            for (int kb = i + 4; kb <= j && !traced; kb += 32 * TB_UNR) {
+                int tr[TB_UNR], myjj[TB_UNR];
+#pragma unroll
+                for (int r = 0; r < TB_UNR; r++) {
+                    const int k = kb + 32 * r + lane;
+                    tr[r] = 0; myjj[r] = k + 1;
+                    if (k <= j) {
+                        int t = f.type(i + 1, k);
+                        if (t) {
+                            const int cc = f.c(i + 1, k) + P->dangle5[t * 5 + f.S1(i)] + f.AU(t);
+                            if (fij == cc + f.f(k + 1)) tr[r] = i + 1;
+                            if (k < n && fij == f.f(k + 2) + cc + P->dangle3[t * 5 + f.S1(k + 1)]) { tr[r] = i + 1; myjj[r] = k + 2; }
+                        }
+                        t = f.type(i, k);
+                        if (t) {
+                            const int cc = f.c(i, k) + f.AU(t);
+                            if (fij == cc + f.f(k + 1)) tr[r] = i;
+                            if (k < n && fij == f.f(k + 2) + cc + P->dangle3[t * 5 + f.S1(k + 1)]) { tr[r] = i; myjj[r] = k + 2; }
+                        }
                     }
                 }
-                const unsigned hit = __ballot_sync(FULL, tr != 0);
-                if (hit) {
-                    const int src = __ffs(hit) - 1;
-                    traced = __shfl_sync(FULL, tr, src);
-                    jj = __shfl_sync(FULL, myjj, src);
-                    kk = kb + src;
-                    break;
+#pragma unroll
+                for (int r = 0; r < TB_UNR; r++) {
+                    const unsigned hit = __ballot_sync(FULL, tr[r] != 0);
+                    if (hit && !traced) {
+                        const int src = __ffs(hit) - 1;
+                        traced = __shfl_sync(FULL, tr[r], src);
+                        jj = __shfl_sync(FULL, myjj[r], src);
+                        kk = kb + 32 * r + src;
+                    }
                 }
             }
             if (!traced) { failed = true; break; }
@@ -233,11 +255,18 @@ __global__ void __launch_bounds__(128) k_traceback(TraceBuffers b)
                 if (lane == 0) { st[i - start] = '('; st[j - start] = ')'; }
             } else {
                 int ksplit = -1;
-                for (int kb = i + 4; kb <= j - 5; kb += 32) {
-                    const int k = kb + lane;
-                    const bool ok = (k <= j - 5) && (fij == f.m(i, k) + f.m(k + 1, j));
-                    const unsigned hit = __ballot_sync(FULL, ok);
-                    if (hit) { ksplit = kb + __ffs(hit) - 1; break; }
+                for (int kb = i + 4; kb <= j - 5 && ksplit < 0; kb += 32 * TB_UNR) {
+                    bool ok[TB_UNR];
+#pragma unroll
+                    for (int r = 0; r < TB_UNR; r++) {
+                        const int k = kb + 32 * r + lane;
+                        ok[r] = (k <= j - 5) && (fij == f.m(i, k) + f.m(k + 1, j));
+                    }
+#pragma unroll
+                    for (int r = 0; r < TB_UNR; r++) {
+                        const unsigned hit = __ballot_sync(FULL, ok[r]);
+                        if (hit && ksplit < 0) ksplit = kb + 32 * r + __ffs(hit) - 1;
+                    }
                 }
                 if (ksplit < 0) { failed = true; break; }
                 PUSH(i, ksplit, 1);
@@ -246,56 +275,62 @@ __global__ void __launch_bounds__(128) k_traceback(TraceBuffers b)
             }
         }
         // "repeat": (i,j) pairs; follow stacks / interior loops until a hairpin or multiloop
-        int cij = f.c(i, j);
         for (;;) {
-            const int t = f.type(i, j);
-            if (cij == tb_hairpin(f, i, j, t)) break;
+            // Speculative helix run: lane l looks at the pair (i+l, j-l).  A pair is left by the stack
+            // (p,q) = (i+1,j-1) -- the first candidate in reference order -- iff it is not closed by a
+            // hairpin and c == stack + c(i+1,j-1); the run ends at the first lane for which that fails,
+            // so a whole helix costs one round trip to the band instead of one per base pair.
+            const int pi = i + lane, pj = j - lane, dl = pj - pi;
+            int tl = 0, cl = MF_INF, hl = 0;
+            if (dl >= 4) {
+                tl = f.type(pi, pj);
+                if (tl) { cl = f.c(pi, pj); hl = tb_hairpin(f, pi, pj, tl); }
+            }
+            const int tn = __shfl_down_sync(FULL, tl, 1), cn = __shfl_down_sync(FULL, cl, 1);
+            const bool cont = tl && tn && lane < 31 && cl != hl && dl >= 6 && cl == P->stack[tl * 8 + P->rtype[tn]] + cn;
+            const int r = __ffs(~__ballot_sync(FULL, cont)) - 1;   // 0..31: first pair of the run that is not left by a stack
+            if (lane >= 1 && lane <= r) { st[pi - start] = '('; st[pj - start] = ')'; }
+            i += r; j -= r;
+            if (r == 31) continue;                                 // lane 31 cannot look ahead: speculate again from there
+            const int cij = __shfl_sync(FULL, cl, r), t = __shfl_sync(FULL, tl, r);
+            if (cij == __shfl_sync(FULL, hl, r)) break;            // hairpin
             const int d = j - i;
             const int K = min(30, d - 6);
-            int np = 0, nq = 0, ncij = 0;
+            int np = 0, nq = 0;
             bool found = false;
-            if (K >= 0) {   // the stack (p,q) = (i+1,j-1) is the first candidate in reference order: test it alone first
-                const int t2 = f.type(i + 1, j - 1);
-                if (t2) {
-                    const int c2 = f.c(i + 1, j - 1);
-                    if (cij == P->stack[t * 8 + P->rtype[t2]] + c2) {
-                        i++; j--; cij = c2;
-                        if (lane == 0) { st[i - start] = '('; st[j - start] = ')'; }
-                        continue;
-                    }
-                }
-            }
             if (K >= 0) {
-                for (int cb = 0; cb < 496; cb += 32) {
-                    const int m = cb + lane;
-                    bool ok = false;
-                    int p = 0, q = 0, cpq = 0;
-                    if (m < 496) {
-                        const int u = P->uv[m][0], v = P->uv[m][1];
-                        if (u + v <= K) {
-                            p = i + 1 + u; q = j - 1 - v;
-                            const int t2 = f.type(p, q);
-                            if (t2) {
-                                cpq = f.c(p, q);
-                                ok = (cij == tb_loop_energy(f, i, j, p, q, t, P->rtype[t2]) + cpq);
+                for (int cb = 0; cb < 496 && !found; cb += 32 * TB_UNR) {
+                    bool ok[TB_UNR];
+                    int p[TB_UNR], q[TB_UNR];
+#pragma unroll
+                    for (int rr = 0; rr < TB_UNR; rr++) {
+                        const int m = cb + 32 * rr + lane;
+                        ok[rr] = false; p[rr] = 0; q[rr] = 0;
+                        if (m < 496) {
+                            const int u = P->uv[m][0], v = P->uv[m][1];
+                            if (u + v <= K) {
+                                p[rr] = i + 1 + u; q[rr] = j - 1 - v;
+                                const int t2 = f.type(p[rr], q[rr]);
+                                if (t2) ok[rr] = (cij == tb_loop_energy(f, i, j, p[rr], q[rr], t, P->rtype[t2]) + f.c(p[rr], q[rr]));
                             }
                         }
                     }
-                    const unsigned hit = __ballot_sync(FULL, ok);
-                    if (hit) {
-                        const int src = __ffs(hit) - 1;
-                        np = __shfl_sync(FULL, p, src);
-                        nq = __shfl_sync(FULL, q, src);
-                        ncij = __shfl_sync(FULL, cpq, src);
-                        found = true;
-                        break;
+#pragma unroll
+                    for (int rr = 0; rr < TB_UNR; rr++) {
+                        const unsigned hit = __ballot_sync(FULL, ok[rr]);
+                        if (hit && !found) {
+                            const int src = __ffs(hit) - 1;
+                            np = __shfl_sync(FULL, p[rr], src);
+                            nq = __shfl_sync(FULL, q[rr], src);
+                            found = true;
+                        }
                     }
                     // rows u > K contribute nothing; entries are u-major, so stop once u exceeds K
-                    if (P->uv[min(cb + 31, 495)][0] > K && P->uv[cb][0] > K) break;
+                    if (P->uv[min(cb + 32 * TB_UNR, 495)][0] > K) break;
                 }
             }
             if (found) {
-                i = np; j = nq; cij = ncij;
+                i = np; j = nq;
                 if (lane == 0) { st[i - start] = '('; st[j - start] = ')'; }
                 continue;
             }
@@ -304,22 +339,28 @@ __global__ void __launch_bounds__(128) k_traceback(TraceBuffers b)
             const int mm = P->MLclosing + P->MLintern[tt];
             const int d5 = P->dangle5[tt * 5 + f.S1(j - 1)], d3 = P->dangle3[tt * 5 + f.S1(i + 1)];
             int ksplit = -1, which = 0;
-            for (int kb = i + 5; kb <= j - 6; kb += 32) {
-                const int k = kb + lane;
-                int w = 0;
-                if (k <= j - 6) {
-                    const int a1 = f.m(i + 1, k), a2 = f.m(i + 2, k), b1 = f.m(k + 1, j - 1), b2 = f.m(k + 1, j - 2);
-                    if (cij == a1 + b1 + mm) w = 1;
-                    else if (cij == a2 + b1 + mm + d3) w = 2;
-                    else if (cij == a1 + b2 + mm + d5) w = 3;
-                    else if (cij == a2 + b2 + mm + d3 + d5) w = 4;
+            for (int kb = i + 5; kb <= j - 6 && ksplit < 0; kb += 32 * TB_UNR) {
+                int w[TB_UNR];
+#pragma unroll
+                for (int rr = 0; rr < TB_UNR; rr++) {
+                    const int k = kb + 32 * rr + lane;
+                    w[rr] = 0;
+                    if (k <= j - 6) {
+                        const int a1 = f.m(i + 1, k), a2 = f.m(i + 2, k), b1 = f.m(k + 1, j - 1), b2 = f.m(k + 1, j - 2);
+                        if (cij == a1 + b1 + mm) w[rr] = 1;
+                        else if (cij == a2 + b1 + mm + d3) w[rr] = 2;
+                        else if (cij == a1 + b2 + mm + d5) w[rr] = 3;
+                        else if (cij == a2 + b2 + mm + d3 + d5) w[rr] = 4;
+                    }
                 }
-                const unsigned hit = __ballot_sync(FULL, w != 0);
-                if (hit) {
-                    const int src = __ffs(hit) - 1;
-                    ksplit = kb + src;
-                    which = __shfl_sync(FULL, w, src);
-                    break;
+#pragma unroll
+                for (int rr = 0; rr < TB_UNR; rr++) {
+                    const unsigned hit = __ballot_sync(FULL, w[rr] != 0);
+                    if (hit && ksplit < 0) {
+                        const int src = __ffs(hit) - 1;
+                        ksplit = kb + 32 * rr + src;
+                        which = __shfl_sync(FULL, w[rr], src);
+                    }
                 }
             }
             if (ksplit < 0) { failed = true; break; }
@@ -418,8 +459,7 @@ cudaError_t launch_emit(const TraceBuffers &b, cudaStream_t st)
 // ------------------------------------------------------------------------------------ pack
 __global__ void __launch_bounds__(128) k_pack(TraceBuffers b, const unsigned long long *__restrict__ ss_off,
                                               const unsigned long long *__restrict__ hit_idx, char *__restrict__ arena,
-                                              int *__restrict__ out_start, int *__restrict__ out_len,
-                                              int *__restrict__ out_energy, unsigned long long *__restrict__ out_ssoff)
+                                              mirfold_hit *__restrict__ out_hits, unsigned long long arena_base)
 {
     const unsigned long long g = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -429,20 +469,19 @@ __global__ void __launch_bounds__(128) k_pack(TraceBuffers b, const unsigned lon
     char *dst = arena + ss_off[g];
     for (int k = lane; k <= len; k += 32) dst[k] = k < len ? src[k] : 0;
     if (lane == 0) {
-        const unsigned long long h = hit_idx[g];
-        out_start[h] = b.tb_start[g];
-        out_len[h] = len;
-        out_energy[h] = b.tb_energy[g];
-        out_ssoff[h] = ss_off[g];
+        // the finished public record (include/mirfold.h): the host only copies the table
+        mirfold_hit h;
+        h.start = b.tb_start[g]; h.len = len; h.mfe_dcal = b.tb_energy[g]; h.reserved = 0;
+        h.ss_off = arena_base + ss_off[g];
+        out_hits[hit_idx[g]] = h;
     }
 }
 
 cudaError_t launch_pack(const TraceBuffers &b, const unsigned long long *ss_off, const unsigned long long *hit_idx,
-                        char *arena, int *out_start, int *out_len, int *out_energy, unsigned long long *out_ssoff,
-                        cudaStream_t st)
+                        char *arena, mirfold_hit *out_hits, unsigned long long arena_base, cudaStream_t st)
 {
     if (b.ntb == 0) return cudaSuccess;
     const unsigned long long blocks = (b.ntb + 3) / 4;
-    k_pack<<<(unsigned)blocks, 128, 0, st>>>(b, ss_off, hit_idx, arena, out_start, out_len, out_energy, out_ssoff);
+    k_pack<<<(unsigned)blocks, 128, 0, st>>>(b, ss_off, hit_idx, arena, out_hits, arena_base);
     return cudaGetLastError();
 }

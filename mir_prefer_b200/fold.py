@@ -36,13 +36,15 @@ class FoldResult:
         self.ss_bytes = int(r.ss_bytes)
         self.stats = r.stats.as_dict()
         self.downloaded = bool(r.ss_arena) or self.nhits == 0
-        self.hit_begin = self.total_mfe_dcal = self.hit_table = self.arena = None
+        self.hit_begin = self.hit_count = self.total_mfe_dcal = self.hit_table = self.arena = None
         if self.downloaded:
             if self.nseq:
-                self.hit_begin = np.ctypeslib.as_array(r.hit_begin, shape=(self.nseq + 1,))
+                self.hit_begin = np.ctypeslib.as_array(r.hit_begin, shape=(self.nseq,))
+                self.hit_count = np.ctypeslib.as_array(r.hit_count, shape=(self.nseq,))
                 self.total_mfe_dcal = np.ctypeslib.as_array(r.total_mfe_dcal, shape=(self.nseq,))
             else:
-                self.hit_begin, self.total_mfe_dcal = np.zeros(1, np.uint64), np.zeros(0, np.int32)
+                self.hit_begin, self.total_mfe_dcal = np.zeros(0, np.uint64), np.zeros(0, np.int32)
+                self.hit_count = np.zeros(0, np.uint32)
             if self.nhits:
                 raw = np.ctypeslib.as_array(C.cast(r.hits, C.POINTER(C.c_uint8)), shape=(self.nhits * C.sizeof(_lib.Hit),))
                 self.hit_table = raw.view(HIT_DTYPE)
@@ -52,7 +54,8 @@ class FoldResult:
 
     def hits(self, r):
         """[(dot_bracket, energy_dcal, start_1based)] of record r."""
-        b, e = int(self.hit_begin[r]), int(self.hit_begin[r + 1])
+        b = int(self.hit_begin[r])
+        e = b + int(self.hit_count[r])
         out = []
         for h in self.hit_table[b:e]:
             o, n = int(h["ss_off"]), int(h["len"])
@@ -64,7 +67,7 @@ class FoldResult:
 
     def close(self):
         if self._ptr is not None:
-            self.hit_begin = self.total_mfe_dcal = self.hit_table = self.arena = None
+            self.hit_begin = self.hit_count = self.total_mfe_dcal = self.hit_table = self.arena = None
             self._lib.mirfold_free_result(self._ptr)
             self._ptr = None
 

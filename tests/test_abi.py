@@ -29,7 +29,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.DuplexQuery) == 40
     assert ctypes.sizeof(_lib.DuplexVerdict) == 48
     assert ctypes.sizeof(_lib.Stats) == 7 * 8 + 6 * 8 + 2 * 4 + 8
-    assert _lib.Result.stats.offset == 56
+    assert _lib.Result.stats.offset == 64
 
 
 def test_no_device_fails_loudly_not_silently():

@@ -176,8 +176,12 @@ def test_chunking_is_invisible(oracle):
 
 
 def _check_structure_properties(res, lens, L):
-    hb = res.hit_begin
+    hb, hc = res.hit_begin.astype(np.int64), res.hit_count.astype(np.int64)
     tab = res.hit_table
+    # the per-record runs tile the hit table exactly once
+    order = np.argsort(hb, kind="stable")
+    nz = order[hc[order] > 0]
+    assert hc.sum() == res.nhits and (hb[nz][1:] == (hb[nz] + hc[nz])[:-1]).all() and (len(nz) == 0 or hb[nz][0] == 0)
     assert (tab["len"] >= 1).all() and (tab["len"] <= L + 3).all()   # window touching the 3' end: up to L*+3 chars
     assert (tab["start"] >= 1).all()
     arena = res.arena
@@ -187,10 +191,11 @@ def _check_structure_properties(res, lens, L):
     nul = np.flatnonzero(arena == 0)
     assert (depth[nul] == 0).all()
     assert set(np.unique(arena).tolist()) <= {0, ord("("), ord(")"), ord(".")}
-    rec_of_hit = np.repeat(np.arange(res.nseq), np.diff(hb).astype(np.int64))
+    rec_of_hit = np.empty(res.nhits, np.int64)
+    rec_of_hit[np.repeat(hb, hc) + (np.arange(res.nhits) - np.repeat(np.cumsum(hc) - hc, hc))] = np.repeat(np.arange(res.nseq), hc)
     assert (tab["start"] + tab["len"] - 1 <= lens[rec_of_hit]).all()
     # every record with n >= 5 prints at least the final backtrack; total MFE <= every hit energy
-    assert (np.diff(hb)[lens >= 5] >= 1).all()
+    assert (hc[lens >= 5] >= 1).all()
     assert (res.total_mfe_dcal[rec_of_hit] <= tab["mfe_dcal"]).all()
     assert (res.total_mfe_dcal <= 0).all()
 
@@ -204,7 +209,8 @@ def test_full_size_properties_and_determinism(mf, oracle):
     def digest(res, order):
         out = [None] * len(order)
         for k, r in enumerate(order):
-            b, e = int(res.hit_begin[k]), int(res.hit_begin[k + 1])
+            b = int(res.hit_begin[k])
+            e = b + int(res.hit_count[k])
             h = hashlib.sha256()
             t = res.hit_table[b:e]   # explicit columns: a multi-field view would drag ss_off along in tobytes()
             h.update(np.stack([t["start"], t["len"], t["mfe_dcal"]]).astype("<i4").tobytes())
