@@ -288,8 +288,9 @@ __device__ __forceinline__ void dev_phase_a16(const unsigned int *Mp, int *rD, S
 
 // Systolic variant of dev_phase_a16 (the default).  The right operand of thread t at split e and strip
 // diagonal s is the word the next row pair t+1 used two splits earlier for diagonal s-2, so only
-// s = 0, 1 are loaded; s = 2..4 arrive by SHFL.DOWN from lane+1's registers of step e-2 (X*/Y* hold the
-// words of the last even/odd step).  3 LDG + 3 SHFL + 5 VIADDMNMX.S16x2 per step instead of 6 LDG + 5:
+// s = 0 is loaded; s = 1 is spliced from the previous step's s = 0 words of this lane and lane+1, and
+// s = 2..4 arrive by SHFL.DOWN from lane+1's registers of step e-2 (X*/Y* hold the words of the last
+// even/odd step).  2 LDG + 4 SHFL + 1 PRMT + 5 VIADDMNMX.S16x2 per step instead of 6 LDG + 5:
 // the strips are bound by L1-miss traffic, not by issue slots.  A warp covers 30 row pairs; lanes 30,
 // 31 are the halo that feeds lanes 28, 29 and are recomputed by the next tile.
 template <int NT, class StrideT>
@@ -338,10 +339,12 @@ __device__ __forceinline__ void dev_phase_a16_sys(const unsigned int *Mp, int *r
         }
         pa += 2 * NS;
         pb += -2 * NS + 1;
-#define MF_SYS_STEP(V0, V1, V2, AOFF, BOFF)                                                        \
+#define MF_SYS_STEP(V0, V1, V2, P0, AOFF, BOFF)                                                    \
     {                                                                                              \
         const unsigned int av = pa[AOFF];                                                          \
-        const unsigned int n0 = pb[BOFF], n1 = pb[(BOFF) + NS];                                    \
+        const unsigned int n0 = pb[BOFF];                                                          \
+        /* s = 1: rows (i, i+1) need the previous step's s = 0 words of rows (i+1, i+2) */         \
+        const unsigned int n1 = __byte_perm(P0, __shfl_down_sync(0xffffffffu, P0, 1), 0x5432);     \
         const unsigned int b2 = __shfl_down_sync(0xffffffffu, V0, 1);                              \
         const unsigned int b3 = __shfl_down_sync(0xffffffffu, V1, 1);                              \
         const unsigned int b4 = __shfl_down_sync(0xffffffffu, V2, 1);                              \
@@ -357,13 +360,13 @@ __device__ __forceinline__ void dev_phase_a16_sys(const unsigned int *Mp, int *r
 #define MF_UNROLL_(n) MF_PRAGMA_(unroll n)
         MF_UNROLL_(MF_SYS_UNROLL)
         for (; e + 1 <= emain; e += 2) {
-            MF_SYS_STEP(X0, X1, X2, 0, 0)
-            MF_SYS_STEP(Y0, Y1, Y2, NS, -NS - H + 1)
+            MF_SYS_STEP(X0, X1, X2, Y0, 0, 0)
+            MF_SYS_STEP(Y0, Y1, Y2, X0, NS, -NS - H + 1)
             pa += 2 * NS;
             pb += -2 * NS + 1;
         }
         if (e <= emain) {
-            MF_SYS_STEP(X0, X1, X2, 0, 0)
+            MF_SYS_STEP(X0, X1, X2, Y0, 0, 0)
             e++;
         }
 #undef MF_SYS_STEP
