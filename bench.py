@@ -284,6 +284,13 @@ def run_ours(args, rank, world, local_rank):
         except Exception:
             hbm_peak, hbm_src = 6650.0, "fallback"
         band_bytes = cells * 8.0  # c + fML written once, int32
+        traffic = None            # dram read+write of the dominant fill launch, from the committed ncu --set full capture
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "fill_traffic.json")))
+            if WORKLOAD == "parity" and args.loci == 10000 and SPAN == 300:
+                traffic = {"bytes_per_launch": tr["dram_bytes_read"] + tr["dram_bytes_write"], "kernel": tr["kernel"], "source": tr["source"]}
+        except Exception:
+            pass
         out = {
             "metric": METRIC, "value": nt_all * args.steps / t_dev, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -306,7 +313,7 @@ def run_ours(args, rank, world, local_rank):
                                         % (peak_a / 1e12, peak_dpx / 1e12),
                          "algorithmic_terms_per_launch": t_alg, "terms_per_cell": t_alg / max(cells, 1), "rho": rho,
                          "kernel_ms": fill_s * 1e3, "kernel_share_of_step": fill_s / (t_dev / args.steps),
-                         "traffic": None,
+                         "traffic": traffic,
                          "hbm": {"bound": "hbm", "achieved": band_bytes / fill_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                  "frac": band_bytes / fill_s / 1e9 / hbm_peak, "peak_source": hbm_src,
                                  "note": "band store of c+fML (8 B/cell) only; the kernel is integer-issue bound"}},
@@ -334,7 +341,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--loci", type=int, default=10000, help="loci per GPU (BASELINE configs[1]: 10000)")
-    ap.add_argument("--ref-loci-per-core", type=int, default=24)
+    ap.add_argument("--ref-loci-per-core", type=int, default=96, help="CPU legs: loci per host core and step (about 10 s of RNALfold)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--workload", default="parity", choices=sorted(WORKLOADS),
                     help="length law of SURVEY 8(d); the bench line of record is the default (parity-10k)")

@@ -1100,6 +1100,10 @@ __global__ void __launch_bounds__(128) k_f3(const LocusDesc *__restrict__ loci, 
                     int j = i + DS;
                     int cj = cd[j], f1 = F[j + 1];
                     const int *pa = C + band_row_base(L, i) + (DS - 4) * NS;   // C(i, i+d), in row i's owner tile
+#ifndef MF_F3_UNROLL
+#define MF_F3_UNROLL 4
+#endif
+                    MF_UNROLL_(MF_F3_UNROLL)
                     for (int d = DS; d <= dend; d++, j++, pa += NS) {
                         const int cj1 = cd[j + 1], f2 = F[j + 2];
                         const int cA = pa[0], cB = pa[1 - NS];      // C(i+1, j) sits one diagonal down, one row up
