@@ -176,7 +176,9 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    per_step = max(cores, min(args.loci, cores * args.ref_loci_per_core))
+    # bounded sample: about 0.12 s of RNALfold per locus, one shard per core; keep the whole run near 100 s
+    per_core = int(max(8, min(args.ref_loci_per_core, 100.0 / (args.steps + 1) / 0.12)))
+    per_step = max(cores, min(args.loci, cores * per_core))
     seqs = workload(0, per_step)
     nt = sum(len(s) for s in seqs)
     for _ in range(min(args.warmup, 1)):
