@@ -339,10 +339,17 @@ __device__ __forceinline__ void dev_phase_a16_sys(const unsigned int *Mp, int *r
         }
         pa += 2 * NS;
         pb += -2 * NS + 1;
-#define MF_SYS_STEP(V0, V1, V2, P0, AOFF, BOFF)                                                    \
+#ifndef MF_SYS_PF
+#define MF_SYS_PF 0   /* L1 prefetch distance of the strip operands in steps (even); 0 = none */
+#endif
+#if MF_SYS_PF > 0
+#define MF_SYS_PREFETCH(a_, b_) if (e + MF_SYS_PF + 1 <= emain) { dev_prefetch_l1(a_); dev_prefetch_l1(b_); }
+#else
+#define MF_SYS_PREFETCH(a_, b_)
+#endif
+#define MF_SYS_COMPUTE(V0, V1, V2, P0, AV, N0)                                                     \
     {                                                                                              \
-        const unsigned int av = pa[AOFF];                                                          \
-        const unsigned int n0 = pb[BOFF];                                                          \
+        const unsigned int av = (AV), n0 = (N0);                                                   \
         /* s = 1: rows (i, i+1) need the previous step's s = 0 words of rows (i+1, i+2) */         \
         const unsigned int n1 = __byte_perm(P0, __shfl_down_sync(0xffffffffu, P0, 1), 0x5432);     \
         const unsigned int b2 = __shfl_down_sync(0xffffffffu, V0, 1);                              \
@@ -353,11 +360,38 @@ __device__ __forceinline__ void dev_phase_a16_sys(const unsigned int *Mp, int *r
         a4 = __viaddmin_s16x2(av, b4, a4);                                                         \
         V0 = n0; V1 = n1; V2 = b2;                                                                 \
     }
+#define MF_SYS_STEP(V0, V1, V2, P0, AOFF, BOFF) MF_SYS_COMPUTE(V0, V1, V2, P0, pa[AOFF], pb[BOFF])
 #ifndef MF_SYS_UNROLL
 #define MF_SYS_UNROLL 2
 #endif
 #define MF_PRAGMA_(x) _Pragma(#x)
 #define MF_UNROLL_(n) MF_PRAGMA_(unroll n)
+#ifdef MF_SYS_PIPE
+        // software pipeline: the eight words of the NEXT four steps are requested before the current four are
+        // consumed, so one L2 round trip overlaps ~55 instructions of shuffles and min-plus instead of preceding them
+        if (e + 7 <= emain) {
+            unsigned int q0 = pa[0], q1 = pb[0], q2 = pa[NS], q3 = pb[-NS - H + 1];
+            unsigned int q4 = pa[2 * NS], q5 = pb[-2 * NS + 1], q6 = pa[3 * NS], q7 = pb[-3 * NS - H + 2];
+            for (; e + 7 <= emain; e += 4) {
+                pa += 4 * NS;
+                pb += -4 * NS + 2;
+                const unsigned int r0 = pa[0], r1 = pb[0], r2 = pa[NS], r3 = pb[-NS - H + 1];
+                const unsigned int r4 = pa[2 * NS], r5 = pb[-2 * NS + 1], r6 = pa[3 * NS], r7 = pb[-3 * NS - H + 2];
+                MF_SYS_COMPUTE(X0, X1, X2, Y0, q0, q1)
+                MF_SYS_COMPUTE(Y0, Y1, Y2, X0, q2, q3)
+                MF_SYS_COMPUTE(X0, X1, X2, Y0, q4, q5)
+                MF_SYS_COMPUTE(Y0, Y1, Y2, X0, q6, q7)
+                q0 = r0; q1 = r1; q2 = r2; q3 = r3; q4 = r4; q5 = r5; q6 = r6; q7 = r7;
+            }
+            MF_SYS_COMPUTE(X0, X1, X2, Y0, q0, q1)
+            MF_SYS_COMPUTE(Y0, Y1, Y2, X0, q2, q3)
+            MF_SYS_COMPUTE(X0, X1, X2, Y0, q4, q5)
+            MF_SYS_COMPUTE(Y0, Y1, Y2, X0, q6, q7)
+            e += 4;
+            pa += 4 * NS;
+            pb += -4 * NS + 2;
+        }
+#endif
         MF_UNROLL_(MF_SYS_UNROLL)
         for (; e + 1 <= emain; e += 2) {
             MF_SYS_STEP(X0, X1, X2, Y0, 0, 0)
@@ -370,6 +404,7 @@ __device__ __forceinline__ void dev_phase_a16_sys(const unsigned int *Mp, int *r
             e++;
         }
 #undef MF_SYS_STEP
+#undef MF_SYS_COMPUTE
         for (; e <= e1; e++) {   // tail: diagonal d+s accepts e <= d+s-5 (s >= 1 only), words loaded directly
             const unsigned int av = Mp[(e - 4) * NS + t];
             const unsigned int *qb = Mp + (d - 5 - e) * NS + ((e & 1) ? t + ((e + 1) >> 1) : H + t + (e >> 1));
@@ -687,8 +722,9 @@ __device__ __forceinline__ int dev_fml16(const DevParams *__restrict__ P, const 
 
 #ifdef MF_TIMELINE   /* per-warp cycle accounting of one CTA (debug builds only: make TIMELINE=1) */
 #define TL_DECL long long tl_acc[6] = {0, 0, 0, 0, 0, 0}; long long tl_t = clock64();
-#define TL_MARK(k) { const long long t_ = clock64(); tl_acc[k] += t_ - tl_t; tl_t = t_; }
-#define TL_DUMP if (blockIdx.x == 3 && lane == 0) printf("TL n=%d warp %2d  dml %8lld  work1 %8lld  bar1 %8lld  work2 %8lld  sync %8lld  other %8lld\n", n, wid, tl_acc[0], tl_acc[1], tl_acc[2], tl_acc[3], tl_acc[4], tl_acc[5]);
+/* the clock read is predicated on a shared-memory word loaded at this point, so it cannot be scheduled across a barrier */
+#define TL_MARK(k) { long long t_ = tl_t; if (*(volatile int *)&sFlag != 0x7fffffff) t_ = clock64(); tl_acc[k] += t_ - tl_t; tl_t = t_; }
+#define TL_DUMP if (blockIdx.x == 3 && lane == 0) printf("TL n=%d warp %2d  dml %8lld  work1 %8lld  bar1 %8lld  work2 %8lld  sync %8lld  dmlsync %8lld\n", n, wid, tl_acc[0], tl_acc[1], tl_acc[2], tl_acc[3], tl_acc[4], tl_acc[5]);
 #else
 #define TL_DECL
 #define TL_MARK(k)
@@ -764,9 +800,10 @@ __global__ void __launch_bounds__(NT, MINB) k_fill_s16(FillLaunch a)
             if (a.opts & 2) dev_phase_a<NT>(Mb, rD, NS, n, it - 1, min(it + 3, dmax), tid, !(a.opts & 1));
             else if (a.opts & 4) dev_phase_a16<NT>(Mp, rD, NS, n, it - 1, min(it + 3, dmax), tid, !(a.opts & 1));
             else dev_phase_a16_sys<NT>(Mp, rD, NS, n, it - 1, min(it + 3, dmax), tid);
+            TL_MARK(0)
             __syncthreads();
+            TL_MARK(5)
         }
-        TL_MARK(0)
         if (wid < NWC) {
             const int d = it;
             if (d <= dmax) {

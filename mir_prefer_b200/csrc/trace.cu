@@ -62,6 +62,9 @@ struct Fold {
     const int *__restrict__ C;
     const int *__restrict__ M;
     const int *__restrict__ F;
+    const unsigned char *pairT;   // shared-memory copies of DevParams::pair / rtype (block-wide)
+    const unsigned char *rtypeT;
+    int AUp;                      // TerminalAU
     int n, Ls, NS;
     // tiled long loci (LocusDesc::tile_*): row i lives in tile min((i-1)/tile_step, tile_last)
     int tile_last, tile_step, dmax;
@@ -72,7 +75,16 @@ struct Fold {
     {
         const int d = j - i;
         if (i < 1 || j > n || d < 4 || d >= Ls) return 0;
-        return P->pair[S(i) * 8 + S(j)];
+        return pairT[S(i) * 8 + S(j)];
+    }
+    // unchecked variants for callers that know 1 <= i, j <= n and 4 <= j-i < Ls (inner cells of a pair)
+    __device__ __forceinline__ int type_nc(int i, int j) const { return pairT[S(i) * 8 + S(j)]; }
+    __device__ __forceinline__ int c_nc(int i, int j) const
+    {
+        const int d = j - i;
+        unsigned long long off = (unsigned)((d - 4) * NS + (i - 1));
+        if (tile_last) off = tb_tiled_off(i, d, tile_rcp, tile_last, tile_step, n, dmax);
+        return C[off];
     }
     __device__ __forceinline__ int band(const int *__restrict__ A, int i, int j) const
     {
@@ -85,7 +97,7 @@ struct Fold {
     __device__ __forceinline__ int c(int i, int j) const { return band(C, i, j); }
     __device__ __forceinline__ int m(int i, int j) const { return band(M, i, j); }
     __device__ __forceinline__ int f(int i) const { return (i >= 1 && i <= n + 2) ? F[i] : 0; }
-    __device__ __forceinline__ int AU(int t) const { return t > 2 ? P->TerminalAU : 0; }
+    __device__ __forceinline__ int AU(int t) const { return t > 2 ? AUp : 0; }
 };
 
 __device__ int tb_loop_energy(const Fold &f, int i, int j, int p, int q, int t, int t2)
@@ -135,6 +147,11 @@ __device__ int tb_hairpin(const Fold &f, int i, int j, int t)
 #endif
 __global__ void __launch_bounds__(128, TB_MINB) k_traceback(TraceBuffers b)
 {
+    __shared__ unsigned char sPairT[64], sRtypeT[8], sUV[496 * 2];
+    if (threadIdx.x < 64) sPairT[threadIdx.x] = b.P->pair[threadIdx.x];
+    if (threadIdx.x < 8) sRtypeT[threadIdx.x] = b.P->rtype[threadIdx.x];
+    for (int k = threadIdx.x; k < 496 * 2; k += 128) sUV[k] = (&b.P->uv[0][0])[k];
+    __syncthreads();
     const unsigned long long g = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (g >= b.ntb) return;
@@ -150,6 +167,7 @@ __global__ void __launch_bounds__(128, TB_MINB) k_traceback(TraceBuffers b)
     const int start = b.tb_start_list[b.list_off[l] + kidx];
     Fold f;
     f.P = b.P; f.C = b.C + L.band_off; f.M = b.M + L.band_off; f.F = b.F + L.seq_off;
+    f.pairT = sPairT; f.rtypeT = sRtypeT; f.AUp = b.P->TerminalAU;
     f.n = L.n; f.Ls = L.Ls; f.NS = L.stride;
     f.tile_last = L.tile_last; f.tile_step = L.tile_step; f.dmax = L.dmax; f.tile_rcp = L.tile_rcp;
     const DevParams *__restrict__ P = b.P;
@@ -282,12 +300,12 @@ __global__ void __launch_bounds__(128, TB_MINB) k_traceback(TraceBuffers b)
             // so a whole helix costs one round trip to the band instead of one per base pair.
             const int pi = i + lane, pj = j - lane, dl = pj - pi;
             int tl = 0, cl = MF_INF, hl = 0;
-            if (dl >= 4) {
-                tl = f.type(pi, pj);
-                if (tl) { cl = f.c(pi, pj); hl = tb_hairpin(f, pi, pj, tl); }
+            if (dl >= 4) {   // (i,j) is a pair inside the band, so every (i+l, j-l) with span >= 4 is addressable
+                tl = f.type_nc(pi, pj);
+                if (tl) { cl = f.c_nc(pi, pj); hl = tb_hairpin(f, pi, pj, tl); }
             }
             const int tn = __shfl_down_sync(FULL, tl, 1), cn = __shfl_down_sync(FULL, cl, 1);
-            const bool cont = tl && tn && lane < 31 && cl != hl && dl >= 6 && cl == P->stack[tl * 8 + P->rtype[tn]] + cn;
+            const bool cont = tl && tn && lane < 31 && cl != hl && dl >= 6 && cl == P->stack[tl * 8 + f.rtypeT[tn]] + cn;
             const int r = __ffs(~__ballot_sync(FULL, cont)) - 1;   // 0..31: first pair of the run that is not left by a stack
             if (lane >= 1 && lane <= r) { st[pi - start] = '('; st[pj - start] = ')'; }
             i += r; j -= r;
@@ -307,11 +325,11 @@ __global__ void __launch_bounds__(128, TB_MINB) k_traceback(TraceBuffers b)
                         const int m = cb + 32 * rr + lane;
                         ok[rr] = false; p[rr] = 0; q[rr] = 0;
                         if (m < 496) {
-                            const int u = P->uv[m][0], v = P->uv[m][1];
-                            if (u + v <= K) {
+                            const int u = sUV[2 * m], v = sUV[2 * m + 1];
+                            if (u + v <= K) {   // span of (p,q) = d-2-u-v >= 4: inside the band
                                 p[rr] = i + 1 + u; q[rr] = j - 1 - v;
-                                const int t2 = f.type(p[rr], q[rr]);
-                                if (t2) ok[rr] = (cij == tb_loop_energy(f, i, j, p[rr], q[rr], t, P->rtype[t2]) + f.c(p[rr], q[rr]));
+                                const int t2 = f.type_nc(p[rr], q[rr]);
+                                if (t2) ok[rr] = (cij == tb_loop_energy(f, i, j, p[rr], q[rr], t, f.rtypeT[t2]) + f.c_nc(p[rr], q[rr]));
                             }
                         }
                     }
@@ -326,7 +344,7 @@ __global__ void __launch_bounds__(128, TB_MINB) k_traceback(TraceBuffers b)
                         }
                     }
                     // rows u > K contribute nothing; entries are u-major, so stop once u exceeds K
-                    if (P->uv[min(cb + 32 * TB_UNR, 495)][0] > K) break;
+                    if (sUV[2 * min(cb + 32 * TB_UNR, 495)] > K) break;
                 }
             }
             if (found) {
@@ -335,7 +353,7 @@ __global__ void __launch_bounds__(128, TB_MINB) k_traceback(TraceBuffers b)
                 continue;
             }
             // multiloop decomposition
-            const int tt = P->rtype[t];
+            const int tt = f.rtypeT[t];
             const int mm = P->MLclosing + P->MLintern[tt];
             const int d5 = P->dangle5[tt * 5 + f.S1(j - 1)], d3 = P->dangle3[tt * 5 + f.S1(i + 1)];
             int ksplit = -1, which = 0;
