@@ -153,6 +153,26 @@ def test_tiled_long_loci_edges(mf, oracle):
     assert_same(mf, oracle, [s], 300)
 
 
+def test_randomized_lengths_and_spans(mf, oracle):
+    """Seeded fuzz over (n, L): bucket boundaries (160/161, 352/353, 608/609), spans that are odd, tiny,
+    equal to n, larger than n, and GC contents from 0.2 to 0.8 -- every record bit-exact vs the oracle."""
+    rng = np.random.default_rng(20261017)
+    edge_n = [5, 6, 9, 31, 32, 33, 159, 160, 161, 351, 352, 353, 607, 608, 609, 640]
+    for L in (7, 37, 99, 161, 300, 353, 401):
+        seqs = []
+        for k in range(14):
+            n = int(edge_n[(k + L) % len(edge_n)]) if k % 2 == 0 else int(rng.integers(5, 700))
+            gc = float(rng.uniform(0.2, 0.8))
+            p = [(1 - gc) / 2, gc / 2, gc / 2, (1 - gc) / 2]
+            s = "".join(rng.choice(list("ACGT"), size=n, p=p))
+            if k % 5 == 0 and n > 60:      # a planted perfect helix: deep energies, long stacks
+                a = "".join(rng.choice(list("GC"), size=int(rng.integers(8, 25))))
+                rc = a[::-1].translate(str.maketrans("GC", "CG"))
+                s = s[:10] + a + "TTCG" + rc + s[10 + 2 * len(a) + 4:]
+            seqs.append(s)
+        assert_same(mf, oracle, seqs, L)
+
+
 def test_against_reference_binary_live(mf, oracle):
     """When the reference's own RNALfold travelled to this box (oracle/_ref), compare against it."""
     if not oracle.have_rlf():
