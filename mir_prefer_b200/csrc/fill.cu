@@ -1057,10 +1057,18 @@ static cudaError_t launch_fill_bucket(const FillLaunch &a, int first, int count,
 
 // Loci arrive sorted by descending DP cells == descending n (for a fixed span), so each stride
 // bucket is a contiguous range [bucket_first[k], bucket_first[k+1]).
-cudaError_t launch_fill(const FillLaunch &a, cudaStream_t st)
+cudaError_t launch_fill(const FillLaunch &a, cudaStream_t st, cudaStream_t side, cudaEvent_t fork, cudaEvent_t join)
 {
     if (a.nloci == 0) return cudaSuccess;
     cudaError_t e = cudaSuccess;
+    // The buckets touch disjoint fill units: the smaller ones run on a side stream so that their CTAs fill
+    // the SMs the last wave of the big bucket leaves idle.
+    const bool fork_small = side != nullptr && (a.bucket_first[4] - a.bucket_first[2]) > 0 && (a.bucket_first[2] - a.bucket_first[0]) > 0;
+    cudaStream_t st2 = fork_small ? side : st;
+    if (fork_small) {
+        if ((e = cudaEventRecord(fork, st)) != cudaSuccess) return e;
+        if ((e = cudaStreamWaitEvent(side, fork, 0)) != cudaSuccess) return e;
+    }
     // generic (n > 608)
     const int ng = a.bucket_first[1] - a.bucket_first[0];
     if (ng > 0) {
@@ -1075,8 +1083,12 @@ cudaError_t launch_fill(const FillLaunch &a, cudaStream_t st)
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
     if ((e = launch_fill_bucket<608, 512, 2>(a, a.bucket_first[1], a.bucket_first[2] - a.bucket_first[1], st)) != cudaSuccess) return e;
-    if ((e = launch_fill_bucket<352, 384, 3>(a, a.bucket_first[2], a.bucket_first[3] - a.bucket_first[2], st)) != cudaSuccess) return e;
-    if ((e = launch_fill_bucket<160, 256, 4>(a, a.bucket_first[3], a.bucket_first[4] - a.bucket_first[3], st)) != cudaSuccess) return e;
+    if ((e = launch_fill_bucket<352, 384, 3>(a, a.bucket_first[2], a.bucket_first[3] - a.bucket_first[2], st2)) != cudaSuccess) return e;
+    if ((e = launch_fill_bucket<160, 256, 4>(a, a.bucket_first[3], a.bucket_first[4] - a.bucket_first[3], st2)) != cudaSuccess) return e;
+    if (fork_small) {
+        if ((e = cudaEventRecord(join, side)) != cudaSuccess) return e;
+        if ((e = cudaStreamWaitEvent(st, join, 0)) != cudaSuccess) return e;
+    }
     return cudaSuccess;
 }
 

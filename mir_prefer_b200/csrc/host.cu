@@ -78,6 +78,7 @@ struct Partial {  // what one device produced for its share of the records
 struct Device {
     int id = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t side = nullptr;     // small fill buckets run here, concurrently with the big one
     DevParams *dP = nullptr;
     size_t mem_budget = 0;
     // pooled buffers
@@ -101,6 +102,8 @@ struct Device {
         dP = nullptr;
         if (stream) cudaStreamDestroy(stream);
         stream = nullptr;
+        if (side) cudaStreamDestroy(side);
+        side = nullptr;
     }
 };
 
@@ -534,7 +537,8 @@ void run_device(Device &D, const char *seqs, const uint64_t *h_off, const std::v
         FillLaunch fa{D.units.as<LocusDesc>(), nu, max_n, D.codes.as<unsigned char>(), D.C.as<int>(), D.M.as<int>(), D.ring.as<int>(),
                       D.Mp.as<unsigned int>(), D.dP, {0, 0, 0, 0, 0}, D.fillflags.as<int>(), force_wide ? 1 : 0, env_opts()};
         for (int b = 0; b < 5; b++) fa.bucket_first[b] = bucket_first[b];
-        CK(launch_fill(fa, st));
+        static const bool no_side = getenv("MIRFOLD_NO_SIDE_STREAM") != nullptr;   // A/B runs
+        CK(launch_fill(fa, st, no_side ? nullptr : D.side, D.ev[10], D.ev[11]));
         CK(cudaEventRecord(D.ev[3], st));
         int n_long = 0;
         while (n_long < nl && hl[n_long].n > MF_TILE_LEN) n_long++;   // sorted by descending cells == descending n
@@ -731,6 +735,7 @@ int mirfold_open(mirfold_ctx **pctx, const int *device_ids, int n_devices, const
         D.id = id;
         cudaError_t e = cudaSetDevice(id);
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&D.stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&D.side, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaMalloc(&D.dP, sizeof(DevParams));
         if (e == cudaSuccess) e = cudaMemcpy(D.dP, hp, sizeof(DevParams), cudaMemcpyHostToDevice);
         if (e == cudaSuccess) e = fill_configure_device();

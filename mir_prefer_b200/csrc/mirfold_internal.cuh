@@ -132,7 +132,8 @@ struct FillLaunch {
 };
 cudaError_t launch_prepare(const char *raw, const LocusDesc *loci, int nloci, unsigned long long total_codes,
                            unsigned char *codes, int *F, cudaStream_t st);
-cudaError_t launch_fill(const FillLaunch &a, cudaStream_t st);
+cudaError_t launch_fill(const FillLaunch &a, cudaStream_t st, cudaStream_t side = nullptr, cudaEvent_t fork = nullptr,
+                        cudaEvent_t join = nullptr);   // side != nullptr: small buckets run concurrently on it
 cudaError_t fill_configure_device();
 cudaError_t launch_f3(const LocusDesc *loci, int nloci, int n_long, int max_Ls, const unsigned char *codes, const int *C, int *F,
                       const DevParams *P, cudaStream_t st);   // first n_long loci: n > MF_TILE_LEN
