@@ -1118,7 +1118,10 @@ __device__ __forceinline__ int dev_f3_term(const unsigned char *sPair, const int
     return best;
 }
 
-__global__ void __launch_bounds__(128) k_f3(const LocusDesc *__restrict__ loci, int nloci,
+#ifndef MF_F3_MINB
+#define MF_F3_MINB 12   /* 40 registers: more resident warps = more band lines in flight (4.2 -> 3.75 ms) */
+#endif
+__global__ void __launch_bounds__(128, MF_F3_MINB) k_f3(const LocusDesc *__restrict__ loci, int nloci,
                                             const unsigned char *__restrict__ codes, const int *__restrict__ Call,
                                             int *__restrict__ Fall, const DevParams *__restrict__ P)
 {
