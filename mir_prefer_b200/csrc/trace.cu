@@ -210,8 +210,19 @@ __global__ void __launch_bounds__(128, TB_MINB) k_traceback(TraceBuffers b)
         j >>= 1;
         if (j < i + 4) continue;
         if (ml == 0) {
-            const int fij = f.f(i);
-            if (fij == f.f(i + 1)) { PUSH(i + 1, j, 0); continue; }
+            // leading unpaired bases: the reference pushes (i+1, j, 0) and pops it again, one base per round
+            // (Lfold.c:501-506); the run of equal f3 values is skipped in one lane-parallel step instead
+            int fij = f.f(i);
+            bool dropped = false;
+            for (;;) {
+                const unsigned eq = __ballot_sync(FULL, f.f(i + 1 + lane) == fij);
+                const int run = (eq == FULL) ? 32 : __ffs(~eq) - 1;
+                if (run == 0) break;
+                i += run;
+                if (j < i + 4) { dropped = true; break; }   // the popped entry would be discarded (Lfold.c:499)
+                // fij is unchanged: f3(i) == f3(i - run) along the run
+            }
+            if (dropped) continue;
             int traced = 0, jj = 0, kk = 0;
             // candidates k = i+4 .. j in reference order; TB_UNR chunks of 32 per round so that the band / f3
             // loads of a round are all in flight together (the scan is latency-bound, not issue-bound)
@@ -255,9 +266,25 @@ __global__ void __launch_bounds__(128, TB_MINB) k_traceback(TraceBuffers b)
                 if (jj == j + 2 && j < n) st[j + 1 - start] = '.';
             }
         } else {
-            const int fij = f.m(i, j);
-            if (f.m(i, j - 1) == fij) { PUSH(i, j - 1, 1); continue; }
-            if (f.m(i + 1, j) == fij) { PUSH(i + 1, j, 1); continue; }
+            // unpaired bases of a multiloop segment: the reference peels one base per push/pop round, 3' side
+            // first, then 5' side (Lfold.c:555-566).  Same order here, but a whole run per step and no stack traffic.
+            int fij = 0;
+            bool dropped = false;
+            for (;;) {
+                if (j < i + 4) { dropped = true; break; }   // the popped entry would be discarded (Lfold.c:499)
+                fij = f.m(i, j);
+                const unsigned eq3 = __ballot_sync(FULL, f.m(i, j - 1 - lane) == fij);
+                if (eq3 & 1u) { j -= (eq3 == FULL) ? 32 : __ffs(~eq3) - 1; continue; }
+                // 5' side: lane l stands for the state after l peels; it stops at the first l whose 5' test fails or
+                // (l >= 1) whose 3' test succeeds -- the outer loop then re-evaluates at that position
+                const bool c5 = f.m(i + 1 + lane, j) == fij;
+                const bool c3 = lane >= 1 && f.m(i + lane, j - 1) == fij;
+                const unsigned go = __ballot_sync(FULL, c5 && !c3);
+                const int run = (go == FULL) ? 32 : __ffs(~go) - 1;
+                if (run == 0) break;
+                i += run;
+            }
+            if (dropped) continue;
             int t = f.type(i, j);
             const int cij = f.c(i, j) + P->MLintern[t];
             t = f.type(i + 1, j);
