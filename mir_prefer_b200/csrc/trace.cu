@@ -143,7 +143,7 @@ __device__ int tb_hairpin(const Fold &f, int i, int j, int t)
 
 // one warp per traceback
 #ifndef TB_MINB
-#define TB_MINB 10
+#define TB_MINB 12
 #endif
 __global__ void __launch_bounds__(128, TB_MINB) k_traceback(TraceBuffers b)
 {
