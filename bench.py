@@ -337,9 +337,13 @@ def run_ours(args, rank, world, local_rank):
             sample = seqs[:sample_n]
             dt, kind, used = cpu_fold_stage(sample, SPAN, cores)
             snt = sum(len(s) for s in sample)
+            one = sample[:12]                                   # also the P=1 figure
+            dt1, _, _ = cpu_fold_stage(one, SPAN, 1)
             out["cpu_baseline"] = {"value": snt / dt, "unit": UNIT, "cores": used, "kind": kind,
                                    "sample": "first %d loci (%d nt) of the same workload, %d concurrent RNALfold -L 300 "
-                                             "processes, %.1f s" % (sample_n, snt, used, dt)}
+                                             "processes, %.1f s" % (sample_n, snt, used, dt),
+                                   "single_core_value": sum(len(x) for x in one) / dt1,
+                                   "dp_cells_per_s": snt / dt * (cells / max(nt, 1))}
         print(json.dumps(out))
     mf.close()
     if world > 1:
