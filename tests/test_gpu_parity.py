@@ -173,6 +173,20 @@ def test_randomized_lengths_and_spans(mf, oracle):
         assert_same(mf, oracle, seqs, L)
 
 
+@pytest.mark.parametrize("pin", json.load(open(os.path.join(GOLDEN, "bulk_pins.json")))["pins"],
+                         ids=lambda p: "%s-%d-L%d" % (p["law"], p["nloci"], p["span"]))
+def test_full_size_configs_match_rnalfold_sha256(mf, pin):
+    """Whole BASELINE configs at (or near) full size: the complete RNALfold-format text has the sha256 of the
+    text the reference's own RNALfold binary produced on the same input (tools/bulk_parity.py, run once on a
+    GPU box with oracle/_ref/RNALfold on all host cores; byte-identical there)."""
+    seqs = synth_loci(pin["seed"], pin["nloci"], pin["law"])
+    text = "".join(">locus%d:%d-%d + 1-22 0 1,22,+\n%s\n" % (k, 1, len(s) + 1, s) for k, s in enumerate(seqs))
+    out = mf.fold_text(text, pin["span"])
+    if "bytes" in pin:
+        assert len(out) == pin["bytes"]
+    assert hashlib.sha256(out.encode()).hexdigest() == pin["sha256"]
+
+
 def test_against_reference_binary_live(mf, oracle):
     """When the reference's own RNALfold travelled to this box (oracle/_ref), compare against it."""
     if not oracle.have_rlf():
