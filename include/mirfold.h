@@ -120,6 +120,17 @@ int mirfold_debug_matrices(mirfold_ctx *ctx, const char *seq, uint32_t n, int sp
 
 void mirfold_free_result(mirfold_result *res);
 
+/* Replaces: what RNALfold's main() prints per record (RLF .rodata "%s (%6.2f) %4d\n" / "%s\n (%6.2f)\n",
+ * SURVEY A.6) -- the text miR_PREFeR.py collects at :3085-3098 and parses at :1541-1599.  For every record r
+ * of `res` (the result of mirfold_fold over the same seqs/seq_off) the block
+ *     <ss> (<mfe>) <start>\n   per hit, in RNALfold's print order
+ *     <sequence token upper-cased, T->U>\n (<total mfe>)\n
+ * is written to one buffer; (*rec_off)[r] .. (*rec_off)[r+1] delimit record r's block (header echo lines are
+ * the caller's).  Host-only, multi-threaded; both buffers are owned by the library until mirfold_free_text(). */
+int mirfold_format_records(const mirfold_result *res, const char *seqs, const uint64_t *seq_off, uint32_t nseq,
+                           char **text, uint64_t **rec_off);
+void mirfold_free_text(char *text, uint64_t *rec_off);
+
 /* Measurement aid (bench.py roofline denominator): sustained rate of independent min-plus terms
  * (one add + one min each) on device 0 of the context, terms per second, for plain add+min code and
  * for the DPX intrinsic __viaddmin_s32. */

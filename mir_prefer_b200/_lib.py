@@ -55,7 +55,7 @@ class DuplexVerdict(C.Structure):
 # every symbol include/mirfold.h declares
 EXPORTS = ["mirfold_open", "mirfold_close", "mirfold_fold", "mirfold_fold_device", "mirfold_debug_matrices",
            "mirfold_free_result", "mirfold_strerror", "mirfold_last_error", "mirfold_version", "mirfold_duplex",
-           "mirfold_duplex_fail_name", "mirfold_int_peak"]
+           "mirfold_duplex_fail_name", "mirfold_int_peak", "mirfold_format_records", "mirfold_free_text"]
 
 _lib = None
 
@@ -81,6 +81,11 @@ def load():
     lib.mirfold_fold_device.restype = C.c_int
     lib.mirfold_debug_matrices.argtypes = [vp, C.c_char_p, C.c_uint32, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.mirfold_debug_matrices.restype = C.c_int
+    lib.mirfold_format_records.argtypes = [C.POINTER(Result), C.c_void_p, C.POINTER(C.c_uint64), C.c_uint32,
+                                           C.POINTER(C.c_void_p), C.POINTER(C.POINTER(C.c_uint64))]
+    lib.mirfold_format_records.restype = C.c_int
+    lib.mirfold_free_text.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+    lib.mirfold_free_text.restype = None
     lib.mirfold_free_result.argtypes = [C.POINTER(Result)]
     lib.mirfold_free_result.restype = None
     lib.mirfold_strerror.argtypes = [C.c_int]

@@ -27,9 +27,10 @@ HIT_DTYPE = np.dtype([("start", "<i4"), ("len", "<i4"), ("mfe_dcal", "<i4"), ("r
 class FoldResult:
     """Owns a mirfold_result.  Hit order inside a record is RNALfold's print order."""
 
-    def __init__(self, lib, ptr, nseq):
+    def __init__(self, lib, ptr, nseq, inputs=None):
         self._lib = lib
         self._ptr = ptr
+        self._inputs = inputs          # (uint8 buffer, uint64 offsets) the result was folded from
         r = ptr.contents
         self.nseq = int(r.nseq)
         self.nhits = int(r.nhits)
@@ -64,6 +65,24 @@ class FoldResult:
 
     def total(self, r):
         return int(self.total_mfe_dcal[r])
+
+    def record_blocks(self):
+        """RNALfold's output of every record (hit lines, converted sequence, total line) as one bytes object
+        plus nseq+1 offsets -- formatted natively by mirfold_format_records() (include/mirfold.h)."""
+        if self._inputs is None or not self.downloaded:
+            raise MirfoldError(-3, "record_blocks() needs a downloaded result of fold()/fold_packed()")
+        buf, off = self._inputs
+        text, rec_off = C.c_void_p(), C.POINTER(C.c_uint64)()
+        rc = self._lib.mirfold_format_records(self._ptr, buf.ctypes.data_as(C.c_void_p), off.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                              self.nseq, C.byref(text), C.byref(rec_off))
+        if rc != 0:
+            raise MirfoldError(rc, self._lib.mirfold_strerror(rc).decode())
+        try:
+            offs = np.ctypeslib.as_array(rec_off, shape=(self.nseq + 1,)).copy() if self.nseq else np.zeros(1, np.uint64)
+            data = C.string_at(text, int(offs[-1]))
+        finally:
+            self._lib.mirfold_free_text(text, rec_off)
+        return data, offs
 
     def close(self):
         if self._ptr is not None:
@@ -165,7 +184,7 @@ class MirFold:
                                     nseq, int(span), int(flags), C.byref(res))
         if rc != 0:
             self._raise(rc)
-        return FoldResult(self._lib, res, nseq)
+        return FoldResult(self._lib, res, nseq, inputs=(buf, off))
 
     def fold(self, seqs, span, flags=0):
         buf, off = self.pack(seqs)
@@ -244,27 +263,33 @@ class MirFold:
         return res
 
     # ---- RNALfold CLI contract -------------------------------------------------------------
-    def fold_text(self, text, span):
-        """RNALfold-identical stdout for RNALfold-style stdin text (`RNALfold -L span`)."""
+    def fold_text_bytes(self, text, span):
+        """RNALfold-identical stdout (bytes) for RNALfold-style stdin text (`RNALfold -L span`)."""
         items = parse_rnalfold_input(text)
         seqs = [tok for kind, tok in items if kind == "seq"]
         out = []
         with self.fold(seqs, span) as res:
+            data, offs = res.record_blocks()
+            view = memoryview(data)
             r = 0
             for kind, tok in items:
                 if kind == "echo":
-                    out.append(tok + "\n")
+                    out.append(tok.encode("utf-8", "surrogateescape") + b"\n")
                 else:
-                    out.append(format_record(tok, res.hits(r), res.total(r)))
+                    out.append(view[int(offs[r]):int(offs[r + 1])])
                     r += 1
-        return "".join(out)
+        return b"".join(out)
+
+    def fold_text(self, text, span):
+        """RNALfold-identical stdout for RNALfold-style stdin text (`RNALfold -L span`)."""
+        return self.fold_text_bytes(text, span).decode("utf-8", "surrogateescape")
 
     def fold_fasta_files(self, fastas, outnames, span):
         """fold_use_RNALfold() replacement: fold every FASTA shard, write RNALfold-format outputs."""
         for fa, outname in zip(fastas, outnames):
-            with open(fa) as f:
+            with open(fa, encoding="utf-8", errors="surrogateescape") as f:   # header bytes pass through unchanged
                 text = f.read()
-            with open(outname + ".tmp", "w") as f:
-                f.write(self.fold_text(text, span))
+            with open(outname + ".tmp", "wb") as f:
+                f.write(self.fold_text_bytes(text, span))
             os.rename(outname + ".tmp", outname)   # atomic, like MP:3098
         return list(outnames)

@@ -19,7 +19,6 @@ What has to stay byte-compatible with the reference, and is pinned by tests:
 from collections import namedtuple
 
 from . import structures as S
-from .fold import format_record
 
 # region / locus are [start, end) in genome coordinates, exactly as dump_piece prints them;
 # peaks = [(start, end, strand)], matures = [(start, end, strand, depth)];
@@ -125,6 +124,7 @@ class RecordFold:
             yield (rec.tag, "%s-%s" % (rec.locus[0], rec.locus[1]), found)
 
     def rnalfold_text(self):
+        data, offs = self.result.record_blocks()
         out = []
         for r, rec in enumerate(self.records):
             out.append(header_line(rec) + "\n")
@@ -132,7 +132,8 @@ class RecordFold:
             if seq.split(None, 1)[:1] == []:      # blank line: echoed, not folded
                 out.append(seq + "\n")
             else:
-                out.append(format_record(seq, self.result.hits(r), self.result.total(r)))
+                b, e = self.result.block(r, offs)
+                out.append(data[b:e].decode("ascii"))
         return "".join(out)
 
     def write_rnalfold_text(self, path):
@@ -177,6 +178,13 @@ class _Replicated:
 
     def total(self, r):
         return self._res.total(self._index[r])
+
+    def record_blocks(self):
+        return self._res.record_blocks()
+
+    def block(self, r, offs):
+        u = self._index[r]
+        return int(offs[u]), int(offs[u + 1])
 
     def close(self):
         self._res.close()

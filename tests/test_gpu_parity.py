@@ -187,6 +187,18 @@ def test_full_size_configs_match_rnalfold_sha256(mf, pin):
     assert hashlib.sha256(out.encode()).hexdigest() == pin["sha256"]
 
 
+def test_native_formatter_equals_python_formatter(mf):
+    """mirfold_format_records() (C, multi-threaded) vs the Python format_record() on every record, including
+    empty / tiny records, lower case and IUPAC letters, and more than 256 records (threaded path)."""
+    from mir_prefer_b200 import format_record
+    seqs = synth_loci(55, 300, (5, 420)) + ["", "acgu", "ACGTNNRYacgtn" * 9, "G" * 30 + "TTCG" + "C" * 30]
+    with mf.fold(seqs, 300) as res:
+        data, offs = res.record_blocks()
+        assert len(offs) == len(seqs) + 1 and int(offs[-1]) == len(data)
+        for r, s in enumerate(seqs):
+            assert data[int(offs[r]):int(offs[r + 1])].decode() == format_record(s, res.hits(r), res.total(r)), r
+
+
 def test_against_reference_binary_live(mf, oracle):
     """When the reference's own RNALfold travelled to this box (oracle/_ref), compare against it."""
     if not oracle.have_rlf():

@@ -47,10 +47,15 @@ t_ref = time.time() - t0
 t0 = time.time()
 with mp.MirFold() as mf:
     got = mf.fold_text(text, span)
-t_gpu = time.time() - t0
+    t_gpu = time.time() - t0
+    t0 = time.time()
+    again = mf.fold_text_bytes(text, span)       # warm: buffers allocated, context up
+    t_warm = time.time() - t0
+    assert again.decode() == got
 nt = sum(len(s) for s in seqs)
 print("config: law=%s nloci=%d span=%d seed=%d  (%d nt)" % (law, nloci, span, seed, nt))
-print("reference RNALfold on %d cores: %.1f s; libmirfold incl. text formatting: %.1f s" % (len(procs), t_ref, t_gpu))
+print("reference RNALfold on %d cores: %.1f s; libmirfold text in -> text out: %.2f s first call (context + allocations), %.2f s warm"
+      % (len(procs), t_ref, t_gpu, t_warm))
 print("bytes  ref %d  ours %d" % (len(want), len(got)))
 print("sha256 ref  %s" % hashlib.sha256(want.encode()).hexdigest())
 print("sha256 ours %s" % hashlib.sha256(got.encode()).hexdigest())
