@@ -131,6 +131,26 @@ int mirfold_format_records(const mirfold_result *res, const char *seqs, const ui
                            char **text, uint64_t **rec_off);
 void mirfold_free_text(char *text, uint64_t *rec_off);
 
+/* Replaces: the structure classification of get_structures_next_extendregion (miR_PREFeR.py:1566-1589) with
+ * is_stem_loop (:1602), filter_ss (:1685) and has_one_good_bifurcation (:1611): for every hit of at least
+ * `minlen` characters the candidate structures the predict stage consumes -- the whole hairpin (sstype 0) or
+ * its outermost-stem pieces longer than 55 that are stem-loops (0) or have one good bifurcation (1).
+ * Structures of record r are out[rec_begin[r] .. rec_begin[r+1]) in the reference's order.  The dot-bracket
+ * string of a structure is ss_arena[ss_off .. ss_off+len) of `res` (NOT NUL-terminated for pieces).
+ * norm_energy = printed energy / length of the whole hit, as in the reference.  Host-only, multi-threaded.
+ * Returns MIRFOLD_ERR_ARG for input on which the reference's functions raise (a hit without any pair). */
+typedef struct mirfold_structure {
+    uint32_t rec;
+    int32_t fold_start;   /* 1-based start of the structure in the record's sequence */
+    int32_t sstype;       /* 0 stem-loop, 1 one good bifurcation */
+    int32_t len;
+    uint64_t ss_off;
+    double norm_energy;
+} mirfold_structure;
+int mirfold_classify(const mirfold_result *res, int minlen, int minloop, mirfold_structure **out, uint64_t *n_out,
+                     uint64_t **rec_begin);
+void mirfold_free_structures(mirfold_structure *s, uint64_t *rec_begin);
+
 /* Measurement aid (bench.py roofline denominator): sustained rate of independent min-plus terms
  * (one add + one min each) on device 0 of the context, terms per second, for plain add+min code and
  * for the DPX intrinsic __viaddmin_s32. */

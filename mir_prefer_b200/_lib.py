@@ -39,6 +39,11 @@ class Result(C.Structure):
                 ("ss_bytes", C.c_uint64), ("total_mfe_dcal", C.POINTER(C.c_int32)), ("stats", Stats)]
 
 
+class Structure(C.Structure):
+    _fields_ = [("rec", C.c_uint32), ("fold_start", C.c_int32), ("sstype", C.c_int32), ("len", C.c_int32),
+                ("ss_off", C.c_uint64), ("norm_energy", C.c_double)]
+
+
 class DuplexQuery(C.Structure):
     _fields_ = [("ss_off", C.c_uint64), ("ss_len", C.c_int32), ("fold_start", C.c_int32),
                 ("mature_start", C.c_int32), ("mature_end", C.c_int32), ("region_start", C.c_int32),
@@ -55,7 +60,8 @@ class DuplexVerdict(C.Structure):
 # every symbol include/mirfold.h declares
 EXPORTS = ["mirfold_open", "mirfold_close", "mirfold_fold", "mirfold_fold_device", "mirfold_debug_matrices",
            "mirfold_free_result", "mirfold_strerror", "mirfold_last_error", "mirfold_version", "mirfold_duplex",
-           "mirfold_duplex_fail_name", "mirfold_int_peak", "mirfold_format_records", "mirfold_free_text"]
+           "mirfold_duplex_fail_name", "mirfold_int_peak", "mirfold_format_records", "mirfold_free_text",
+           "mirfold_classify", "mirfold_free_structures"]
 
 _lib = None
 
@@ -86,6 +92,11 @@ def load():
     lib.mirfold_format_records.restype = C.c_int
     lib.mirfold_free_text.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
     lib.mirfold_free_text.restype = None
+    lib.mirfold_classify.argtypes = [C.POINTER(Result), C.c_int, C.c_int, C.POINTER(C.POINTER(Structure)),
+                                     C.POINTER(C.c_uint64), C.POINTER(C.POINTER(C.c_uint64))]
+    lib.mirfold_classify.restype = C.c_int
+    lib.mirfold_free_structures.argtypes = [C.POINTER(Structure), C.POINTER(C.c_uint64)]
+    lib.mirfold_free_structures.restype = None
     lib.mirfold_free_result.argtypes = [C.POINTER(Result)]
     lib.mirfold_free_result.restype = None
     lib.mirfold_strerror.argtypes = [C.c_int]

@@ -66,6 +66,12 @@ class FoldResult:
     def total(self, r):
         return int(self.total_mfe_dcal[r])
 
+    def classify(self, minlen, minloop=3):
+        """Candidate structures of every record, classified natively (mirfold_classify): a list per record of
+        (norm_energy, fold_start, ss, sstype) -- the tuples get_structures_next_extendregion() builds
+        (miR_PREFeR.py:1566-1589)."""
+        return classify_result(self._lib, self._ptr, self.nseq, self.arena, minlen, minloop)
+
     def record_blocks(self):
         """RNALfold's output of every record (hit lines, converted sequence, total line) as one bytes object
         plus nseq+1 offsets -- formatted natively by mirfold_format_records() (include/mirfold.h)."""
@@ -101,6 +107,31 @@ class FoldResult:
             self.close()
         except Exception:
             pass
+
+
+STRUCT_DTYPE = np.dtype([("rec", "<u4"), ("fold_start", "<i4"), ("sstype", "<i4"), ("len", "<i4"), ("ss_off", "<u8"),
+                         ("norm_energy", "<f8")])
+
+
+def classify_result(lib, res_ptr, nseq, arena, minlen, minloop=3):
+    """mirfold_classify() over a mirfold_result; `arena` is the result's ss_arena as a uint8 array."""
+    out, n_out, rec_begin = C.POINTER(_lib.Structure)(), C.c_uint64(), C.POINTER(C.c_uint64)()
+    rc = lib.mirfold_classify(res_ptr, int(minlen), int(minloop), C.byref(out), C.byref(n_out), C.byref(rec_begin))
+    if rc != 0:
+        raise MirfoldError(rc, "mirfold_classify: a hit without any base pair (the reference's filter_ss raises KeyError here)")
+    try:
+        n = int(n_out.value)
+        rb = np.ctypeslib.as_array(rec_begin, shape=(nseq + 1,)).copy() if nseq else np.zeros(1, np.uint64)
+        tab = np.ctypeslib.as_array(C.cast(out, C.POINTER(C.c_uint8)), shape=(max(n, 1) * C.sizeof(_lib.Structure),)).view(STRUCT_DTYPE)[:n].copy()
+    finally:
+        lib.mirfold_free_structures(out, rec_begin)
+    raw = arena.tobytes() if n else b""
+    ne, fs, ty, ln, so = (tab[k].tolist() for k in ("norm_energy", "fold_start", "sstype", "len", "ss_off"))
+    per_rec = []
+    for r in range(nseq):
+        b, e = int(rb[r]), int(rb[r + 1])
+        per_rec.append([(ne[k], fs[k], raw[so[k]:so[k] + ln[k]].decode("ascii"), ty[k]) for k in range(b, e)])
+    return per_rec
 
 
 def convert_sequence(tok):

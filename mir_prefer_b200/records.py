@@ -113,14 +113,19 @@ class RecordFold:
         self.records = records
         self.result = result
 
-    def structures(self, minlen, minloop=3):
+    def structures(self, minlen, minloop=3, native=True):
         """Generator of (which, peak, [(norm_energy, fold_start, ss, sstype)]) -- one per record,
-        input order: what get_structures_next_extendregion(rnalfoldoutname, minlen) yields."""
+        input order: what get_structures_next_extendregion(rnalfoldoutname, minlen) yields.
+        native=True classifies with libmirfold's mirfold_classify(); False uses the Python rules."""
+        per_unique = self.result.classify(minlen, minloop) if native else None
         for r, rec in enumerate(self.records):
-            found = []
-            for ss, e, start in self.result.hits(r):
-                if len(ss) >= minlen:
-                    found.extend(S.classify(ss, e, start, minloop))
+            if native:
+                found = list(per_unique[self.result.unique_index(r)])
+            else:
+                found = []
+                for ss, e, start in self.result.hits(r):
+                    if len(ss) >= minlen:
+                        found.extend(S.classify(ss, e, start, minloop))
             yield (rec.tag, "%s-%s" % (rec.locus[0], rec.locus[1]), found)
 
     def rnalfold_text(self):
@@ -181,6 +186,12 @@ class _Replicated:
 
     def record_blocks(self):
         return self._res.record_blocks()
+
+    def classify(self, minlen, minloop=3):
+        return self._res.classify(minlen, minloop)
+
+    def unique_index(self, r):
+        return self._index[r]
 
     def block(self, r, offs):
         u = self._index[r]

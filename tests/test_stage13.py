@@ -41,6 +41,89 @@ def test_classifier_matches_reference(stage1):
     assert n > 20
 
 
+def _result_from_rnalfold_text(path):
+    """A mirfold_result built on the host from an RNALfold output file (no GPU): what mirfold_fold() would have
+    returned for that input -- lets the native classifier be checked against the reference fixture on CPU."""
+    import ctypes as C
+    import re
+    import numpy as np
+    from mir_prefer_b200 import _lib
+    energy = re.compile(r"\(\s*(-?[0-9]+[\.]?[0-9]*)\s*\)")
+    recs, cur = [], None
+    for line in open(path):
+        sp = line.strip().split()
+        if line.startswith(">"):
+            cur = []
+            recs.append(cur)
+        elif len(sp) >= 3 and cur is not None:
+            cur.append((sp[0], int(round(float(energy.search(line).group(1)) * 100)), int(sp[-1])))
+    nseq = len(recs)
+    nh = sum(len(r) for r in recs)
+    hits = (_lib.Hit * max(nh, 1))()
+    hb = np.zeros(nseq + 1, np.uint64)
+    hc = np.zeros(nseq + 1, np.uint32)
+    arena = bytearray()
+    k = 0
+    for r, rec in enumerate(recs):
+        hb[r], hc[r] = k, len(rec)
+        for ss, e, start in rec:
+            hits[k].start, hits[k].len, hits[k].mfe_dcal, hits[k].ss_off = start, len(ss), e, len(arena)
+            arena += ss.encode() + b"\0"
+            k += 1
+    arena_arr = np.frombuffer(bytes(arena), np.uint8).copy()
+    totals = np.zeros(max(nseq, 1), np.int32)
+    res = _lib.Result()
+    res.nseq, res.nhits = nseq, nh
+    res.hit_begin = hb.ctypes.data_as(C.POINTER(C.c_uint64))
+    res.hit_count = hc.ctypes.data_as(C.POINTER(C.c_uint32))
+    res.hits = C.cast(hits, C.POINTER(_lib.Hit))
+    res.ss_arena = arena_arr.ctypes.data_as(C.c_void_p)
+    res.ss_bytes = len(arena)
+    res.total_mfe_dcal = totals.ctypes.data_as(C.POINTER(C.c_int32))
+    return res, (hits, hb, hc, arena_arr, totals), nseq, arena_arr
+
+
+def test_native_classifier_matches_reference_tuples(stage1):
+    """mirfold_classify() (C++, host) on the golden RNALfold output vs the reference parser's own tuples."""
+    import ctypes as C
+    from mir_prefer_b200 import _lib
+    from mir_prefer_b200.fold import classify_result
+    lib = _lib.load()
+    res, keep, nseq, arena = _result_from_rnalfold_text(os.path.join(GOLDEN, "synth8.L300.out"))
+    got = classify_result(lib, C.pointer(res), nseq, arena, 55, 3)
+    want = stage1["synth8.L300"]
+    assert len(got) == len(want) and sum(len(g) for g in got) > 50
+    for g, w in zip(got, want):
+        assert [[float.hex(e), s, ss, t] for e, s, ss, t in g] == w["structures"]
+    # the classifier unit vectors (every golden structure): same decisions as the Python rules
+    for item in stage1["classifier"]:
+        ss = item["ss"]
+        assert S.classify(ss, -1234, 7) == _native_classify_one(lib, ss, -1234, 7)
+    with pytest.raises(Exception):
+        _native_classify_one(lib, "." * 60, -100, 1)       # the reference raises KeyError on a pairless hit
+
+
+def _native_classify_one(lib, ss, e, start):
+    import ctypes as C
+    import numpy as np
+    from mir_prefer_b200 import _lib
+    from mir_prefer_b200.fold import classify_result
+    hits = (_lib.Hit * 1)()
+    hits[0].start, hits[0].len, hits[0].mfe_dcal, hits[0].ss_off = start, len(ss), e, 0
+    hb, hc = np.zeros(2, np.uint64), np.array([1, 0], np.uint32)
+    arena = np.frombuffer(ss.encode() + b"\0", np.uint8).copy()
+    tot = np.zeros(1, np.int32)
+    res = _lib.Result()
+    res.nseq, res.nhits = 1, 1
+    res.hit_begin = hb.ctypes.data_as(C.POINTER(C.c_uint64))
+    res.hit_count = hc.ctypes.data_as(C.POINTER(C.c_uint32))
+    res.hits = C.cast(hits, C.POINTER(_lib.Hit))
+    res.ss_arena = arena.ctypes.data_as(C.c_void_p)
+    res.ss_bytes = len(arena)
+    res.total_mfe_dcal = tot.ctypes.data_as(C.POINTER(C.c_int32))
+    return classify_result(lib, C.pointer(res), 1, arena, 1, 3)[0]
+
+
 def test_classifier_error_behaviour_matches_reference():
     with pytest.raises(KeyError):
         S.filter_ss("." * 60)            # reference: dict_pair[-1]
@@ -81,7 +164,21 @@ def test_structures_from_result_equals_file_parser(mf, tmp_path):
     out.write_text(mf.fold_text(text, 300))
     with mf.fold(seqs, 300) as res:
         direct = list(S.structures_from_result(headers, res, 55, 3))
+        native = list(S.structures_from_result_native(headers, res, 55, 3))
     assert direct == list(S.get_structures_next_extendregion(str(out), 55, 3))
+    assert native == direct
+
+
+@pytest.mark.gpu
+def test_native_classifier_at_scale(mf):
+    """mirfold_classify() vs the Python rules on 600 folded loci (threaded path, > 256 records)."""
+    from corpus import synth_loci
+    seqs = synth_loci(77, 600, "parity")
+    headers = [">c:%d-%d + 1-22 0 1,22,+" % (k, k + len(s)) for k, s in enumerate(seqs)]
+    with mf.fold(seqs, 300) as res:
+        native = list(S.structures_from_result_native(headers, res, 55, 3))
+        direct = list(S.structures_from_result(headers, res, 55, 3))
+    assert native == direct and sum(len(x[2]) for x in native) > 5000
 
 
 @pytest.mark.gpu
