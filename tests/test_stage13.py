@@ -154,6 +154,61 @@ def test_live_against_reference_when_present():
         assert tuple(ns["filter_ss"](ss)) == tuple(S.filter_ss(ss))
 
 
+def _random_structure(rng):
+    """A balanced dot-bracket string of 56..300 chars: random nesting, multiloops, several outermost stems."""
+    def helix(depth):
+        arm = int(rng.integers(2, 12))
+        if depth <= 0 or rng.random() < 0.45:
+            inner = "." * int(rng.integers(3, 12))
+        else:
+            inner = "".join("." * int(rng.integers(0, 6)) + helix(depth - 1) for _ in range(int(rng.integers(1, 4))))
+            inner += "." * int(rng.integers(0, 6))
+        lb, rb = int(rng.integers(0, 4)), int(rng.integers(0, 4))
+        return "(" * arm + "." * lb + inner + "." * rb + ")" * arm
+    s = "." * int(rng.integers(0, 8))
+    for _ in range(int(rng.integers(1, 4))):
+        s += helix(int(rng.integers(0, 4))) + "." * int(rng.integers(0, 8))
+    return s
+
+
+def test_native_and_python_classifier_on_random_structures():
+    """3 000 random balanced structures: mirfold_classify() == the Python rules, and -- in the build container --
+    == the reference's own is_stem_loop / filter_ss / has_one_good_bifurcation applied the way its parser does."""
+    import numpy as np
+    from mir_prefer_b200 import _lib
+    lib = _lib.load()
+    ns = None
+    if os.path.exists("/root/reference/miR_PREFeR.py"):
+        import sys
+        sys.path.insert(0, GOLDEN)
+        import ref_extract
+        ns = ref_extract.load()
+    rng = np.random.default_rng(77)
+    n = kinds = 0
+    while n < 3000:
+        ss = _random_structure(rng)
+        if not 56 <= len(ss) <= 300:
+            continue
+        n += 1
+        e, start = -int(rng.integers(0, 9000)), int(rng.integers(1, 300))
+        want = S.classify(ss, e, start)
+        assert _native_classify_one(lib, ss, e, start) == want
+        kinds += len(want)
+        if ns is not None:
+            ne = float("%.2f" % (e / 100.)) / len(ss)
+            ref = []
+            if ns["is_stem_loop"](ss, 3):
+                ref.append((ne, start, ss, 0))
+            else:
+                for off, sub in ns["filter_ss"](ss)[0]:
+                    if ns["is_stem_loop"](sub, 3):
+                        ref.append((ne, start + off, sub, 0))
+                    elif ns["has_one_good_bifurcation"](sub):
+                        ref.append((ne, start + off, sub, 1))
+            assert ref == want
+    assert kinds > 300
+
+
 @pytest.mark.gpu
 def test_structures_from_result_equals_file_parser(mf, tmp_path):
     """Stage 1 without the text round trip == the reference-style parse of the RNALfold text."""
