@@ -331,6 +331,20 @@ def run_ours(args, rank, world, local_rank):
                                  "frac": band_bytes / fill_s / 1e9 / hbm_peak, "peak_source": hbm_src,
                                  "note": "band store of c+fML (8 B/cell) only; the kernel is integer-issue bound"}},
         }
+        if world == 1:
+            # the reference-compatible boundaries on the same batch (informational, outside the timed regions):
+            # RNALfold text in -> byte-identical text out, and the stage-1 candidate-structure tuples
+            text = "".join(">locus%d:%d-%d + 1-22 0 1,22,+\n%s\n" % (k, 1, len(x) + 1, x) for k, x in enumerate(seqs))
+            mf.fold_text_bytes(text, SPAN)
+            t0 = time.perf_counter()
+            nbytes = len(mf.fold_text_bytes(text, SPAN))
+            t_text = time.perf_counter() - t0
+            with mf.fold_packed(host_buf, off, SPAN) as r:
+                t0 = time.perf_counter()
+                nstruct = sum(len(x) for x in r.classify(55))
+                t_cls = time.perf_counter() - t0
+            out["drop_in"] = {"rnalfold_text_in_out_ms": 1e3 * t_text, "text_bytes": nbytes,
+                              "classify_structures_ms": 1e3 * t_cls, "structures": nstruct}
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
             sample_n = max(cores, min(args.loci, cores * args.ref_loci_per_core))
