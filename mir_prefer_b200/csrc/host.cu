@@ -623,7 +623,6 @@ void run_device(Device &D, const char *seqs, const uint64_t *h_off, const std::v
                 CK(cudaMemcpyAsync(out.hits.as<mirfold_hit>() + hbase, D.o_hits.p, nhits * sizeof(mirfold_hit), cudaMemcpyDeviceToHost, st));
             // hit index at each locus boundary: hitidx[tb_base[l]] (device gather -> reuse scan_in)
             {
-                // gather kernel inline via thrust-free lambda: small kernel below
                 k_gather_bounds<<<(nl + 1 + 255) / 256, 256, 0, st>>>(tb.tb_base, D.hitidx.as<unsigned long long>(),
                                                                       D.scan_in.as<unsigned long long>(), nl);
                 CK(cudaGetLastError());
