@@ -543,7 +543,11 @@ void run_device(Device &D, const char *seqs, const uint64_t *h_off, const std::v
         int n_long = 0;
         while (n_long < nl && hl[n_long].n > MF_TILE_LEN) n_long++;   // sorted by descending cells == descending n
         CK(launch_f3(dl, nl, n_long, max_Ls, D.codes.as<unsigned char>(), D.C.as<int>(), D.F.as<int>(), D.dP, st));
-        out.st.kernel_launches += n_long > 0 && n_long < nl ? 1 : 0;
+        {   // kernels launched so far: k_prepare, the fill kernels (16-bit + 32-bit redo per non-empty bucket, generic), k_f3 / k_f3_cta
+            int nfill = bucket_first[1] > bucket_first[0] ? 1 : 0;
+            for (int b = 1; b < 4; b++) if (bucket_first[b + 1] > bucket_first[b]) nfill += force_wide ? 1 : 2;
+            out.st.kernel_launches += 1 + nfill + (n_long > 0 ? 1 : 0) + (n_long < nl ? 1 : 0);
+        }
         CK(cudaEventRecord(D.ev[4], st));
         // ---- K4: plan
         TraceBuffers tb{};
@@ -562,7 +566,7 @@ void run_device(Device &D, const char *seqs, const uint64_t *h_off, const std::v
         CK(cudaStreamSynchronize(st));
         const unsigned long long ntb = hs[0];
         out.st.tracebacks += ntb;
-        out.st.kernel_launches += 6;
+        out.st.kernel_launches += 4;   // k_plan, k_widen_counts, cub scan (init + scan)
         ht.mark("K1-K3 enqueue + plan sync");
         // ---- traceback
         tb.ntb = ntb;
