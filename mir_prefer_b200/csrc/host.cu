@@ -125,10 +125,10 @@ struct ResultOwner {  // lives right behind the public struct
     std::vector<uint64_t> hit_begin;
     std::vector<uint32_t> hit_count;
     HBuf hits;                 // single-device fast path: pinned hit table moved from the Partial
-    std::vector<mirfold_hit> hits_v;   // multi-device path: concatenated
+    mirfold_hit *hits_m = nullptr;     // multi-device path: concatenated (malloc)
     std::vector<int32_t> totals;
     HBuf arena;               // single-device fast path: pinned arena moved from the Partial
-    std::vector<char> arena_v;  // multi-device path: concatenated
+    char *arena_m = nullptr;    // multi-device path: concatenated (malloc)
 };
 
 // ------------------------------------------------------------------ narrow-kernel schedule
@@ -847,30 +847,41 @@ static int fold_impl(mirfold_ctx *ctx, const char *seqs, const uint64_t *seq_off
             parts[0].hits = HBuf();
             R->pub.hits = R->hits.as<mirfold_hit>();
         } else {
-            R->hits_v.resize(nhits);
+            // multi-device: one table and one arena for the caller; every device's part is copied (and its
+            // ss_off rebased) by its own thread into uninitialised buffers -- no zero fill, no serial pass
+            R->hits_m = (mirfold_hit *)malloc(sizeof(mirfold_hit) * (size_t)(nhits ? nhits : 1));
+            R->arena_m = (char *)malloc((size_t)abytes + 1);
+            if (!R->hits_m || !R->arena_m) {
+                free(R->hits_m); free(R->arena_m);
+                for (auto &p : parts) { p.arena.release(); p.hits.release(); }
+                delete R;
+                return MIRFOLD_ERR_NOMEM;
+            }
+            std::vector<std::thread> th;
+            for (int g = 0; g < G; g++)
+                th.emplace_back([&, g] {
+                    const mirfold_hit *src = parts[g].hits.as<mirfold_hit>();
+                    mirfold_hit *dst = R->hits_m + hit_base[g];
+                    const uint64_t ab = arena_base[g];
+                    for (uint64_t h = 0; h < parts[g].nhits; h++) { dst[h] = src[h]; dst[h].ss_off += ab; }
+                    if (parts[g].arena_bytes) memcpy(R->arena_m + ab, parts[g].arena.p, parts[g].arena_bytes);
+                });
+            for (auto &t : th) t.join();
+            R->arena_m[abytes] = 0;
             for (int g = 0; g < G; g++) {
-                const mirfold_hit *src = parts[g].hits.as<mirfold_hit>();
-                mirfold_hit *dst = R->hits_v.data() + hit_base[g];
-                for (uint64_t h = 0; h < parts[g].nhits; h++) { dst[h] = src[h]; dst[h].ss_off += arena_base[g]; }
                 std::lock_guard<std::mutex> lk(ctx->pool_mu);
                 ctx->hits_pool.push_back(parts[g].hits);
                 parts[g].hits = HBuf();
+                ctx->arena_pool.push_back(parts[g].arena);
+                parts[g].arena = HBuf();
             }
-            R->pub.hits = R->hits_v.data();
+            R->pub.hits = R->hits_m;
+            R->pub.ss_arena = R->arena_m;
         }
         if (G == 1) {
             R->arena = parts[0].arena;  // pinned buffer moves into the result
             parts[0].arena = HBuf();
             R->pub.ss_arena = R->arena.as<char>();
-        } else {
-            R->arena_v.resize(abytes + 1);
-            for (int g = 0; g < G; g++) {
-                if (parts[g].arena_bytes) memcpy(R->arena_v.data() + arena_base[g], parts[g].arena.p, parts[g].arena_bytes);
-                std::lock_guard<std::mutex> lk(ctx->pool_mu);
-                ctx->arena_pool.push_back(parts[g].arena);
-                parts[g].arena = HBuf();
-            }
-            R->pub.ss_arena = R->arena_v.data();
         }
         R->pub.ss_bytes = abytes;
     } else {
@@ -925,6 +936,8 @@ void mirfold_free_result(mirfold_result *res)
     }
     R->arena.release();
     R->hits.release();
+    free(R->hits_m);
+    free(R->arena_m);
     delete R;
 }
 
