@@ -341,10 +341,18 @@ def run_ours(args, rank, world, local_rank):
             t_text = time.perf_counter() - t0
             with mf.fold_packed(host_buf, off, SPAN) as r:
                 t0 = time.perf_counter()
-                nstruct = sum(len(x) for x in r.classify(55))
+                per_rec = r.classify(55)
+                nstruct = sum(len(x) for x in per_rec)
                 t_cls = time.perf_counter() - t0
+            # stage 3 on the same structures: one synthetic 21-nt mature on the 5' arm of every structure
+            queries = [(ss, (fs + 8, fs + 29), fs, 1, lens[k] + 1, "+") for k, recs_ in enumerate(per_rec) for (_, fs, ss, _) in recs_]
+            t0 = time.perf_counter()
+            verdicts = mf.duplex(queries)
+            t_dup = time.perf_counter() - t0
             out["drop_in"] = {"rnalfold_text_in_out_ms": 1e3 * t_text, "text_bytes": nbytes,
-                              "classify_structures_ms": 1e3 * t_cls, "structures": nstruct}
+                              "classify_structures_ms": 1e3 * t_cls, "structures": nstruct,
+                              "duplex_queries_ms": 1e3 * t_dup, "duplex_queries": len(queries),
+                              "duplex_pass": sum(1 for v in verdicts if not isinstance(v, str))}
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
             sample_n = max(cores, min(args.loci, cores * args.ref_loci_per_core))

@@ -109,6 +109,12 @@ class FoldResult:
             pass
 
 
+DUPLEX_QUERY_DTYPE = np.dtype([("ss_off", "<u8"), ("ss_len", "<i4"), ("fold_start", "<i4"), ("mature_start", "<i4"),
+                               ("mature_end", "<i4"), ("region_start", "<i4"), ("region_end", "<i4"), ("strand", "<i4"),
+                               ("reserved", "<i4")])
+DUPLEX_VERDICT_DTYPE = np.dtype([(n, "<i4") for n in ("code", "star_start", "star_end", "fold_start", "fold_end", "star_ss_begin",
+                                                     "star_ss_end", "mature_ss_begin", "mature_ss_end", "prime5", "total_dots",
+                                                     "total_bps")])
 STRUCT_DTYPE = np.dtype([("rec", "<u4"), ("fold_start", "<i4"), ("sstype", "<i4"), ("len", "<i4"), ("ss_off", "<u8"),
                          ("norm_energy", "<f8")])
 
@@ -264,33 +270,50 @@ class MirFold:
         nq = len(queries)
         if nq == 0:
             return []
+        # columns are built with numpy (a ctypes field store per value costs more than the kernel)
         offs, parts, pos = {}, [], 0
-        qarr = (_lib.DuplexQuery * nq)()
-        for k, (ss, mature, foldstart, rs, re_, strand) in enumerate(queries):
-            if ss not in offs:
-                offs[ss] = pos
+        ss_off = np.empty(nq, np.uint64)
+        for k, q in enumerate(queries):
+            ss = q[0]
+            o = offs.get(ss)
+            if o is None:
+                o = offs[ss] = pos
                 parts.append(ss)
                 pos += len(ss) + 1
-            q = qarr[k]
-            q.ss_off, q.ss_len, q.fold_start = offs[ss], len(ss), int(foldstart)
-            q.mature_start, q.mature_end = int(mature[0]), int(mature[1])
-            q.region_start, q.region_end, q.strand = int(rs), int(re_), ord(strand)
+            ss_off[k] = o
+        qarr = np.zeros(nq, DUPLEX_QUERY_DTYPE)
+        qarr["ss_off"] = ss_off
+        qarr["ss_len"] = [len(q[0]) for q in queries]
+        qarr["fold_start"] = [q[2] for q in queries]
+        qarr["mature_start"] = [q[1][0] for q in queries]
+        qarr["mature_end"] = [q[1][1] for q in queries]
+        qarr["region_start"] = [q[3] for q in queries]
+        qarr["region_end"] = [q[4] for q in queries]
+        qarr["strand"] = [ord(q[5]) for q in queries]
         arena = ("\0".join(parts) + "\0").encode("ascii")
-        out = (_lib.DuplexVerdict * nq)()
-        rc = self._lib.mirfold_duplex(self._ctx, arena, len(arena), qarr, nq, out)
+        out = np.zeros(nq, DUPLEX_VERDICT_DTYPE)
+        rc = self._lib.mirfold_duplex(self._ctx, arena, len(arena), qarr.ctypes.data_as(C.POINTER(_lib.DuplexQuery)), nq,
+                                      out.ctypes.data_as(C.POINTER(_lib.DuplexVerdict)))
         if rc != 0:
             self._raise(rc)
+        cols = {name: out[name].tolist() for name in DUPLEX_VERDICT_DTYPE.names}
+        code = cols["code"]
+        names = {}
         res = []
-        for k, (ss, mature, foldstart, rs, re_, strand) in enumerate(queries):
-            v = out[k]
-            if v.code != 0:
-                name = self._lib.mirfold_duplex_fail_name(v.code).decode()
-                if v.code == 100:
+        for k, q in enumerate(queries):
+            c = code[k]
+            if c != 0:
+                name = names.get(c)
+                if name is None:
+                    name = names[c] = self._lib.mirfold_duplex_fail_name(c).decode()
+                if c == 100:
                     raise MirfoldError(-3, "duplex query %d: %s (the reference raises here)" % (k, name))
                 res.append(name)
             else:
-                res.append((v.star_start, v.star_end, v.fold_start, v.fold_end, ss[v.star_ss_begin:v.star_ss_end],
-                            bool(v.prime5), ss[v.mature_ss_begin:v.mature_ss_end], v.total_dots, v.total_bps))
+                ss = q[0]
+                res.append((cols["star_start"][k], cols["star_end"][k], cols["fold_start"][k], cols["fold_end"][k],
+                            ss[cols["star_ss_begin"][k]:cols["star_ss_end"][k]], bool(cols["prime5"][k]),
+                            ss[cols["mature_ss_begin"][k]:cols["mature_ss_end"][k]], cols["total_dots"][k], cols["total_bps"][k]))
         return res
 
     # ---- RNALfold CLI contract -------------------------------------------------------------
