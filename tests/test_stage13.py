@@ -103,6 +103,49 @@ def test_native_classifier_matches_reference_tuples(stage1):
         _native_classify_one(lib, "." * 60, -100, 1)       # the reference raises KeyError on a pairless hit
 
 
+def test_native_formatter_reproduces_rnalfold_text_on_cpu():
+    """mirfold_format_records() fed with the hits / totals parsed back from a golden RNALfold output must print
+    that output again, byte for byte (no GPU involved: the result struct is built on the host)."""
+    import ctypes as C
+    import re
+    import numpy as np
+    from mir_prefer_b200 import _lib
+    lib = _lib.load()
+    path = os.path.join(GOLDEN, "synth8.L300.out")
+    res, keep, nseq, arena = _result_from_rnalfold_text(path)
+    # the converted sequence and the total line of every record
+    energy = re.compile(r"\(\s*(-?[0-9]+[\.]?[0-9]*)\s*\)")
+    blocks, seqs, totals, cur = [], [], [], None
+    lines = open(path).read().split("\n")
+    for k, line in enumerate(lines):
+        if line.startswith(">"):
+            cur = []
+            blocks.append(cur)
+        elif cur is not None and line != "":
+            cur.append(line)
+            if re.fullmatch(r" \(\s*-?[0-9.]+\)", line):
+                totals.append(int(round(float(energy.search(line).group(1)) * 100)))
+                seqs.append(cur[-2])
+    assert len(seqs) == nseq == len(totals)
+    tot = np.array(totals, np.int32)
+    res.total_mfe_dcal = tot.ctypes.data_as(C.POINTER(C.c_int32))
+    raw = "".join(s.replace("U", "T").lower() if k % 2 else s for k, s in enumerate(seqs)).encode()   # conversion is the formatter's job
+    off = np.zeros(nseq + 1, np.uint64)
+    off[1:] = np.cumsum([len(s) for s in seqs])
+    buf = np.frombuffer(raw, np.uint8).copy()
+    text, rec_off = C.c_void_p(), C.POINTER(C.c_uint64)()
+    rc = lib.mirfold_format_records(C.pointer(res), buf.ctypes.data_as(C.c_void_p), off.ctypes.data_as(C.POINTER(C.c_uint64)), nseq,
+                                    C.byref(text), C.byref(rec_off))
+    assert rc == 0
+    try:
+        offs = np.ctypeslib.as_array(rec_off, shape=(nseq + 1,)).copy()
+        data = C.string_at(text, int(offs[-1])).decode()
+    finally:
+        lib.mirfold_free_text(text, rec_off)
+    for r in range(nseq):
+        assert data[int(offs[r]):int(offs[r + 1])] == "\n".join(blocks[r]) + "\n", r
+
+
 def _native_classify_one(lib, ss, e, start):
     import ctypes as C
     import numpy as np
