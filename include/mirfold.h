@@ -14,6 +14,8 @@
  * Ownership: inputs are borrowed for the duration of the call; results are owned by the
  * library until mirfold_free_result().  A context is single-caller (one host thread).
  * Results are deterministic and independent of device count and batch composition.
+ * Lifetime: a result may outlive its context -- mirfold_close() with results still alive releases the
+ * devices at once and the context's host bookkeeping when the last result is freed.
  */
 #ifndef MIRFOLD_H
 #define MIRFOLD_H
@@ -32,6 +34,7 @@ extern "C" {
 #define MIRFOLD_ERR_BACKTRACK (-5)   /* traceback found no decomposition (the reference
                                         aborts with "backtrack failed ...")            */
 #define MIRFOLD_ERR_NOMEM (-6)
+#define MIRFOLD_ERR_CALLBACK (-7)    /* a mirfold_chunk_fn returned non-zero             */
 
 /* The only parameter set with a runnable oracle: Turner 1999 as compiled into ViennaRNA
  * 1.8.5, dangles=1, 37 C, tetraloop bonus on (what `RNALfold -L n` uses by default). */
@@ -42,6 +45,10 @@ extern "C" {
  * -320 kcal/mol inside one window) with the 32-bit kernel; MIRFOLD_FLAG_WIDE forces the 32-bit kernel
  * for every locus.  Results are identical either way. */
 #define MIRFOLD_FLAG_WIDE 1u
+/* MIRFOLD_FLAG_SERIAL: run the chunks of a device one after the other on a single lane (no overlap of one chunk's
+ * traceback / download with the next chunk's band fill).  Measurement aid: per-stage device times of
+ * mirfold_stats are only disjoint in this mode.  Results are identical. */
+#define MIRFOLD_FLAG_SERIAL 2u
 
 typedef struct mirfold_ctx mirfold_ctx;
 
@@ -120,6 +127,48 @@ int mirfold_debug_matrices(mirfold_ctx *ctx, const char *seq, uint32_t n, int sp
 
 void mirfold_free_result(mirfold_result *res);
 
+/* Replaces: the chunk loop of fold_use_RNALfold()/gen_next_chunk (miR_PREFeR.py:3022-3044, :3085-3098), which
+ * folds a shard 2*CHECKPOINT_SIZE lines at a time and appends each chunk's text to the output file so that the
+ * whole result never sits in memory.  Same fold as mirfold_fold(), but the results are handed to `fn` chunk by
+ * chunk while later chunks are still computing; a chunk's buffers are only valid during the call.  Chunks are
+ * delivered in the order the devices finish them (NOT input order; `record[k]` names the input record), one
+ * callback at a time; every input record appears in exactly one chunk (records shorter than 5 nt, which have
+ * no hits and a total of 0, arrive in a final chunk without hits).  A non-zero return value of `fn` aborts
+ * the fold with MIRFOLD_ERR_CALLBACK.  ss_off of a chunk's hits is relative to the chunk's own ss_arena. */
+typedef struct mirfold_chunk {
+    uint32_t n_records;
+    int32_t device;                /* CUDA ordinal that produced the chunk (-1 for the final hit-less chunk) */
+    const uint32_t *record;        /* n_records input record indices                                         */
+    const uint64_t *hit_begin;     /* n_records: hits of entry k are hits[hit_begin[k] .. +hit_count[k])      */
+    const uint32_t *hit_count;
+    const int32_t *total_mfe_dcal; /* n_records                                                              */
+    uint64_t nhits;
+    const mirfold_hit *hits;
+    const char *ss_arena;
+    uint64_t ss_bytes;
+} mirfold_chunk;
+typedef int (*mirfold_chunk_fn)(void *user, const mirfold_chunk *chunk);
+int mirfold_fold_stream(mirfold_ctx *ctx, const char *seqs, const uint64_t *seq_off, uint32_t nseq, int span_L,
+                        uint32_t flags, mirfold_chunk_fn fn, void *user, mirfold_stats *stats /* may be NULL */);
+
+/* Device-resident batches: the records are sharded over the context's devices (as mirfold_fold does) and their
+ * raw sequences uploaded once; mirfold_batch_fold() then runs the whole pipeline on every device from HBM.
+ * download = 0 leaves the results in HBM (*out carries stats, nhits and ss_bytes only) -- the kernel-only
+ * measurement of bench.py on any number of devices; download = 1 returns the same result as mirfold_fold(). */
+typedef struct mirfold_batch mirfold_batch;
+int mirfold_batch_upload(mirfold_ctx *ctx, const char *seqs, const uint64_t *seq_off, uint32_t nseq, int span_L,
+                         mirfold_batch **out);
+int mirfold_batch_fold(mirfold_ctx *ctx, mirfold_batch *batch, uint32_t flags, int download, mirfold_result **out);
+void mirfold_batch_free(mirfold_batch *batch);
+
+/* Replaces: the split of the candidate FASTA into NUM_OF_CORE shards by locus count (miR_PREFeR.py:1329-1354)
+ * that decides which RNALfold process folds which record (miR_PREFeR.py:3113-3118).  Here: greedy
+ * longest-processing-time assignment by DP cells, exactly the plan mirfold_fold() uses for a
+ * context of n_shards devices.  Host-only (needs no device and no context).  shard_of[r] = shard of record r;
+ * shard_cells[g] = DP cells assigned to shard g (either output may be NULL). */
+int mirfold_plan_shards(const uint64_t *seq_off, uint32_t nseq, int span_L, int n_shards, uint32_t *shard_of,
+                        uint64_t *shard_cells);
+
 /* Replaces: what RNALfold's main() prints per record (RLF .rodata "%s (%6.2f) %4d\n" / "%s\n (%6.2f)\n",
  * SURVEY A.6) -- the text miR_PREFeR.py collects at :3085-3098 and parses at :1541-1599.  For every record r
  * of `res` (the result of mirfold_fold over the same seqs/seq_off) the block
@@ -155,6 +204,8 @@ void mirfold_free_structures(mirfold_structure *s, uint64_t *rec_begin);
  * (one add + one min each) on device 0 of the context, terms per second, for plain add+min code and
  * for the DPX intrinsic __viaddmin_s32. */
 int mirfold_int_peak(mirfold_ctx *ctx, double *addmin_terms_per_s, double *dpx_terms_per_s);
+/* The same plus the packed 16-bit form the narrow fill kernel issues (VIADDMNMX.S16x2: two terms per instruction). */
+int mirfold_int_peak2(mirfold_ctx *ctx, double *addmin_terms_per_s, double *dpx_terms_per_s, double *s16x2_terms_per_s);
 
 const char *mirfold_strerror(int code);
 /* Human-readable detail of the last error raised in this context (CUDA error string etc). */

@@ -39,6 +39,16 @@ class Result(C.Structure):
                 ("ss_bytes", C.c_uint64), ("total_mfe_dcal", C.POINTER(C.c_int32)), ("stats", Stats)]
 
 
+class Chunk(C.Structure):
+    _fields_ = [("n_records", C.c_uint32), ("device", C.c_int32), ("record", C.POINTER(C.c_uint32)),
+                ("hit_begin", C.POINTER(C.c_uint64)), ("hit_count", C.POINTER(C.c_uint32)),
+                ("total_mfe_dcal", C.POINTER(C.c_int32)), ("nhits", C.c_uint64), ("hits", C.POINTER(Hit)),
+                ("ss_arena", C.c_void_p), ("ss_bytes", C.c_uint64)]
+
+
+CHUNK_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(Chunk))
+
+
 class Structure(C.Structure):
     _fields_ = [("rec", C.c_uint32), ("fold_start", C.c_int32), ("sstype", C.c_int32), ("len", C.c_int32),
                 ("ss_off", C.c_uint64), ("norm_energy", C.c_double)]
@@ -61,7 +71,8 @@ class DuplexVerdict(C.Structure):
 EXPORTS = ["mirfold_open", "mirfold_close", "mirfold_fold", "mirfold_fold_device", "mirfold_debug_matrices",
            "mirfold_free_result", "mirfold_strerror", "mirfold_last_error", "mirfold_version", "mirfold_duplex",
            "mirfold_duplex_fail_name", "mirfold_int_peak", "mirfold_format_records", "mirfold_free_text",
-           "mirfold_classify", "mirfold_free_structures"]
+           "mirfold_classify", "mirfold_free_structures", "mirfold_fold_stream", "mirfold_batch_upload", "mirfold_batch_fold",
+           "mirfold_batch_free", "mirfold_plan_shards", "mirfold_int_peak2"]
 
 _lib = None
 
@@ -112,5 +123,19 @@ def load():
     lib.mirfold_duplex_fail_name.restype = C.c_char_p
     lib.mirfold_int_peak.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.mirfold_int_peak.restype = C.c_int
+    lib.mirfold_int_peak2.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.mirfold_int_peak2.restype = C.c_int
+    lib.mirfold_fold_stream.argtypes = [vp, C.c_void_p, C.POINTER(C.c_uint64), C.c_uint32, C.c_int, C.c_uint32, CHUNK_FN, C.c_void_p,
+                                        C.POINTER(Stats)]
+    lib.mirfold_fold_stream.restype = C.c_int
+    lib.mirfold_batch_upload.argtypes = [vp, C.c_void_p, C.POINTER(C.c_uint64), C.c_uint32, C.c_int, C.POINTER(vp)]
+    lib.mirfold_batch_upload.restype = C.c_int
+    lib.mirfold_batch_fold.argtypes = [vp, vp, C.c_uint32, C.c_int, C.POINTER(C.POINTER(Result))]
+    lib.mirfold_batch_fold.restype = C.c_int
+    lib.mirfold_batch_free.argtypes = [vp]
+    lib.mirfold_batch_free.restype = None
+    lib.mirfold_plan_shards.argtypes = [C.POINTER(C.c_uint64), C.c_uint32, C.c_int, C.c_int, C.POINTER(C.c_uint32),
+                                        C.POINTER(C.c_uint64)]
+    lib.mirfold_plan_shards.restype = C.c_int
     _lib = lib
     return lib

@@ -61,6 +61,7 @@ __global__ void __launch_bounds__(128) k_duplex(const char *__restrict__ arena, 
             lastbp = k;
             if (k < l1 - 2) mend = k;
         }
+    if (partner[lastbp] < 0 || partner[firstbp] < 0) FAIL(DPX_EXC);   // unmatched '(': dict_bp[...] raises KeyError (MP:1932-1933)
     const int star_start = partner[lastbp] - (l1 - 1 - lastbp) + 2;
     const int star_end = partner[firstbp] + (firstbp - l0) + 3;
     V.star_ss_begin = star_start; V.star_ss_end = star_end;
@@ -72,7 +73,7 @@ __global__ void __launch_bounds__(128) k_duplex(const char *__restrict__ arena, 
         if (l0 - star_end < 3) FAIL(5);
         if (star_start < 0) FAIL(6);
     }
-    if (mend < 0) FAIL(DPX_EXC);
+    if (mend < 0 || partner[mend] < 0) FAIL(DPX_EXC);                   // dict_bp[mend] raises (MP:1949)
     const int sstart = partner[mend], send = partner[firstbp];
     const int Lm = mend + 1 - l0, Lsd = max(0, send + 1 - sstart);
     int dots_m = 0, dots_s = 0;

@@ -1,16 +1,22 @@
-// host.cu -- libmirfold host runtime: contexts, memory pools, chunked pipeline, multi-GPU sharding
-// and the C ABI declared in include/mirfold.h.
+// host.cu -- libmirfold host runtime: contexts, memory pools, the two-lane chunk pipeline, multi-GPU
+// sharding and the fold entry points of the C ABI declared in include/mirfold.h.
 //
 // Replaces fold_use_RNALfold()/fold() (/root/reference/miR_PREFeR.py:3047-3119): where the reference
-// forks one RNALfold process per FASTA shard, this runtime shards records over GPUs by DP work
-// (no collectives: loci are independent), runs K1..K4 per chunk on one stream per device, and
-// gathers hit records back in input order.  There is no CPU fallback.
+// forks one RNALfold process per FASTA shard and folds it 2*CHECKPOINT_SIZE lines at a time, this
+// runtime shards records over GPUs by DP work (no collectives: loci are independent), cuts every
+// shard into chunks and keeps two chunks in flight per device on two "lanes" (complete buffer sets):
+// while one lane runs f3 / traceback / pack / download of chunk k on a high-priority stream, the other
+// lane's band fill of chunk k+1 already occupies the SMs the last wave of chunk k left idle.  Results
+// are downloaded straight into buffers shared by all devices of the call (no merge pass) or handed
+// to a callback chunk by chunk (mirfold_fold_stream).  There is no CPU fallback.
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -20,9 +26,10 @@
 
 #include "../../include/mirfold.h"
 #include "mirfold_internal.cuh"
-#include "turner99_v185_tables.inc"
 
-#define MIRFOLD_VERSION "0.1.0"
+#define MIRFOLD_VERSION "0.2.0"
+
+void build_params(DevParams &P);   // params.cu
 
 namespace {
 
@@ -36,7 +43,7 @@ struct DBuf {  // grow-only device buffer
         p = nullptr; cap = 0;
         size_t want = bytes + bytes / 8 + 256;
         cudaError_t e = cudaMalloc(&p, want);
-        if (e != cudaSuccess) { e = cudaMalloc(&p, bytes); want = bytes; }
+        if (e != cudaSuccess) { cudaGetLastError(); e = cudaMalloc(&p, bytes); want = bytes; }
         if (e == cudaSuccess) cap = want;
         return e;
     }
@@ -53,7 +60,7 @@ struct HBuf {  // grow-only pinned host buffer
         if (p) cudaFreeHost(p);
         p = nullptr; cap = 0;
         size_t want = bytes + bytes / 8 + 256;
-        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocPortable);
         if (e == cudaSuccess) cap = want;
         return e;
     }
@@ -61,49 +68,87 @@ struct HBuf {  // grow-only pinned host buffer
     template <class T> T *as() const { return (T *)p; }
 };
 
-struct Partial {  // what one device produced for its share of the records
-    std::vector<uint32_t> recs;            // record ids handled (n >= 5 only)
-    std::vector<uint64_t> rec_hit_begin;   // per handled record: first hit in `hits`
-    std::vector<uint32_t> rec_hit_count;
-    std::vector<int32_t> rec_total;
-    HBuf hits;                             // pinned mirfold_hit[nhits], locus order; ss_off relative to arena
-    uint64_t nhits = 0;
-    HBuf arena;                            // pinned
-    uint64_t arena_bytes = 0;
-    mirfold_stats st{};
-    int err = MIRFOLD_OK;
-    std::string errmsg;
+struct Locus {
+    uint32_t rec;
+    int n;
+    uint64_t cells;
 };
 
-struct Device {
-    int id = 0;
-    cudaStream_t stream = nullptr;
-    cudaStream_t side = nullptr;     // small fill buckets run here, concurrently with the big one
-    DevParams *dP = nullptr;
-    size_t mem_budget = 0;
-    // pooled buffers
-    std::vector<LocusDesc> units_host;   // fill units of the current chunk (pageable: uploaded with a synchronous-staging memcpy)
-    DBuf units;
-    DBuf raw, loci, codes, F, C, M, Mp, ring, fillflags, tbcount, tbbase, listoff, startlist, scan_in, scan_out, scan_tmp;
+// host-side description of one chunk on a lane
+struct Prep {
+    size_t cb = 0, ce = 0;   // [cb, ce) into the device's locus list
+    int nl = 0, nu = 0, max_n = 0, max_Ls = 0, n_long = 0;
+    int bucket_first[5] = {0, 0, 0, 0, 0};
+    unsigned long long seq_acc = 0, band_acc = 0, raw_acc = 0, list_acc = 0, ring_acc = 0;
+};
+
+struct OverflowChunk {   // a chunk that did not fit the shared result buffers (capacity is an estimate)
+    HBuf hits, arena;
+    ~OverflowChunk() { hits.release(); arena.release(); }
+    uint64_t nhits = 0, abytes = 0;
+    std::vector<uint32_t> recs, count;
+    std::vector<uint64_t> begin;
+};
+
+// A lane = one complete set of pipeline buffers and streams; a device alternates chunks between two lanes.
+struct Lane {
+    cudaStream_t s_lo = nullptr;   // uploads, encode, band fill
+    cudaStream_t s_hi = nullptr;   // f3, plan, traceback, pack, downloads (high priority: gets freed SM slots first)
+    cudaStream_t side = nullptr;   // small fill buckets run here, concurrently with the big one
+    DBuf units, raw, loci, codes, F, C, M, Mp, ring, fillflags, tbcount, tbbase, listoff, startlist, scan_in, scan_out, scan_tmp;
     DBuf slots, tblen, tbstart, tblocus, tbflag, tbenergy, stackscr, fail, ssoff, hitidx;
-    DBuf o_hits, o_arena;
-    HBuf h_raw, h_loci, h_listoff, h_small, h_out;
-    cudaEvent_t ev[12] = {};
+    DBuf o_hits, o_arena, bounds, totals;
+    HBuf h_raw, h_loci, h_units, h_listoff, h_small, h_out, h_hits, h_arena;
+    cudaEvent_t ev[12] = {};   // 0 h2d begin, 1 kernels begin, 2 fill begin, 3 fill end, 4 f3 end, 5 pack end, 6 d2h end, 7 done, 10/11 side fork/join
+    // chunk in flight
+    bool pending = false;
+    Prep prep;
+    TraceBuffers tb{};
+    uint64_t nhits = 0, abytes = 0, hit_base = 0, arena_base = 0;
+    std::unique_ptr<OverflowChunk> ovf;
+    std::vector<uint32_t> s_rec, s_count;   // stream sink: per-record tables handed to the callback
+    std::vector<uint64_t> s_begin;
+    std::vector<int32_t> s_total;
+    cudaError_t create(int prio_hi)
+    {
+        cudaError_t e = cudaStreamCreateWithFlags(&s_lo, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&s_hi, cudaStreamNonBlocking, prio_hi);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking);
+        for (auto &x : ev) if (e == cudaSuccess) e = cudaEventCreate(&x);
+        return e;
+    }
     void release()
     {
         DBuf *all[] = {&units, &raw, &loci, &codes, &F, &C, &M, &Mp, &ring, &fillflags, &tbcount, &tbbase, &listoff, &startlist, &scan_in,
                        &scan_out, &scan_tmp, &slots, &tblen, &tbstart, &tblocus, &tbflag, &tbenergy, &stackscr, &fail,
-                       &ssoff, &hitidx, &o_hits, &o_arena};
+                       &ssoff, &hitidx, &o_hits, &o_arena, &bounds, &totals};
         for (DBuf *b : all) b->release();
-        HBuf *hall[] = {&h_raw, &h_loci, &h_listoff, &h_small, &h_out};
+        HBuf *hall[] = {&h_raw, &h_loci, &h_units, &h_listoff, &h_small, &h_out, &h_hits, &h_arena};
         for (HBuf *b : hall) b->release();
         for (auto &e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
+        if (s_lo) cudaStreamDestroy(s_lo);
+        if (s_hi) cudaStreamDestroy(s_hi);
+        if (side) cudaStreamDestroy(side);
+        s_lo = s_hi = side = nullptr;
+    }
+};
+
+struct Device {
+    int id = 0;
+    DevParams *dP = nullptr;
+    size_t mem_budget = 0;
+    Lane lane[2];
+    cudaEvent_t ev_first = nullptr, ev_last = nullptr;
+    DBuf duplex_arena, duplex_q, duplex_v;   // mirfold_duplex scratch
+    void release()
+    {
+        lane[0].release(); lane[1].release();
+        duplex_arena.release(); duplex_q.release(); duplex_v.release();
+        if (ev_first) cudaEventDestroy(ev_first);
+        if (ev_last) cudaEventDestroy(ev_last);
+        ev_first = ev_last = nullptr;
         if (dP) cudaFree(dP);
         dP = nullptr;
-        if (stream) cudaStreamDestroy(stream);
-        stream = nullptr;
-        if (side) cudaStreamDestroy(side);
-        side = nullptr;
     }
 };
 
@@ -115,6 +160,20 @@ struct mirfold_ctx {
     std::vector<HBuf> arena_pool;  // pinned arenas returned by mirfold_free_result
     std::vector<HBuf> hits_pool;   // pinned hit tables returned by mirfold_free_result
     std::mutex pool_mu;
+    int live_results = 0;          // results not yet freed (guarded by pool_mu)
+    bool closed = false;           // mirfold_close() was called; the last mirfold_free_result deletes the context
+    double arena_per_nt = 30.0;    // capacity estimates of the shared result buffers, raised when a call overflows them
+    double hits_per_nt = 0.20;
+};
+
+struct mirfold_batch {
+    mirfold_ctx *ctx = nullptr;
+    uint32_t nseq = 0;
+    int span_L = 0;
+    std::vector<uint64_t> h_off;                   // copy of the caller's offsets
+    std::vector<std::vector<uint32_t>> shard;      // per device, descending DP cells
+    std::vector<uint64_t> raw_off;                 // per record: offset inside its device's buffer
+    std::vector<void *> d_raw;                     // per device
 };
 
 namespace {
@@ -124,138 +183,52 @@ struct ResultOwner {  // lives right behind the public struct
     mirfold_ctx *ctx;
     std::vector<uint64_t> hit_begin;
     std::vector<uint32_t> hit_count;
-    HBuf hits;                 // single-device fast path: pinned hit table moved from the Partial
-    mirfold_hit *hits_m = nullptr;     // multi-device path: concatenated (malloc)
     std::vector<int32_t> totals;
-    HBuf arena;               // single-device fast path: pinned arena moved from the Partial
-    char *arena_m = nullptr;    // multi-device path: concatenated (malloc)
+    HBuf hits, arena;   // pinned, written directly by the devices' downloads
 };
 
-// ------------------------------------------------------------------ narrow-kernel schedule
-// Word-terms of the 16-bit pair ring (see k_fill_s16).  For a cell on diagonal d, pair slot m
-// (0..15) holds the inner diagonals of loop sizes (s_lo, s_hi) = (2m, 2m-1) for even d and
-// (2m+1, 2m) for odd d.  A word-term is (ring, m, x-offset): generic terms read Cm at row offset u
-// for both sizes; bulges read c+AU at offset 0 (5' side unpaired = 0) as pairs and at offset s
-// (3' side) as single halves.  The bank class of a word-term is (xoff - 17 m) mod 32 and lane = class,
-// so every unrolled iteration is one conflict-free LDS.
-void build_s16_schedule(DevParams &P)
-{
-    const int ninio = T99_F_ninio37[2], maxninio = T99_MAX_NINIO;
-    struct Term { int m, xo, ring, clo, chi; bool vlo, vhi; };
-    auto generic_ok = [](int s, int u) { const int v = s - u; return s >= 0 && s <= 30 && u >= 1 && v >= 1 && !(u <= 2 && v <= 2); };
-    auto gconst = [&](int s, int u) { return T99_internal_loop37[s] + std::min(maxninio, std::abs(2 * u - s) * ninio); };
-    for (int par = 0; par < 2; par++) {
-        std::vector<Term> G[32], B[32];
-        for (int m = 0; m < 16; m++) {
-            const int slo = par ? 2 * m + 1 : 2 * m, shi = par ? 2 * m : 2 * m - 1;
-            for (int u = 1; u <= 30; u++) {
-                const bool a = generic_ok(slo, u), b = generic_ok(shi, u);
-                if (a || b) G[((u - MF16_SKEW * m) % 32 + 32) % 32].push_back({m, u, 0, a ? gconst(slo, u) : 0, b ? gconst(shi, u) : 0, a, b});
-            }
-            const bool a = slo >= 2 && slo <= 30, b = shi >= 2 && shi <= 30;
-            if (a || b)
-                B[((0 - MF16_SKEW * m) % 32 + 32) % 32].push_back({m, 0, 1, a ? T99_bulge37[slo] - MF16_DBIAS : 0, b ? T99_bulge37[shi] - MF16_DBIAS : 0, a, b});
-            if (a) B[((slo - MF16_SKEW * m) % 32 + 32) % 32].push_back({m, slo, 1, T99_bulge37[slo] - MF16_DBIAS, 0, true, false});
-            if (b) B[((shi - MF16_SKEW * m) % 32 + 32) % 32].push_back({m, shi, 1, 0, T99_bulge37[shi] - MF16_DBIAS, false, true});
-        }
-        for (int lane = 0; lane < 32; lane++) {
-            std::stable_sort(G[lane].begin(), G[lane].end(), [](const Term &x, const Term &y) { return (x.vlo && x.vhi) < (y.vlo && y.vhi); });
-            int nmask = 0;
-            for (const Term &t : G[lane]) nmask += !(t.vlo && t.vhi);
-            if ((int)G[lane].size() > MF16_NQG || (int)B[lane].size() > MF16_NQB || nmask > MF16_NMG) {
-                fprintf(stderr, "mirfold: 16-bit schedule overflow (par %d lane %d: %zu generic, %zu bulge, %d masked)\n", par, lane,
-                        G[lane].size(), B[lane].size(), nmask);
-                abort();
-            }
-            auto put = [&](int q, const Term *t) {
-                if (t) {
-                    P.s16_td[par][q][lane] = (unsigned)t->m | ((unsigned)t->xo << 4) | ((unsigned)t->ring << 10);
-                    P.s16_cst[par][q][lane] = ((unsigned)t->clo & 0xffffu) | ((unsigned)t->chi << 16);
-                } else {   // no term: read the all-INF row at a lane-private bank
-                    P.s16_td[par][q][lane] = (unsigned)lane << 4 | 1u << 11;
-                    P.s16_cst[par][q][lane] = 0;
-                }
-                const unsigned mk = t ? ((t->vlo ? 0xffffu : 0u) | (t->vhi ? 0xffff0000u : 0u)) : 0xffffffffu;
-                if (q < MF16_NMG) P.s16_mk[par][q][lane] = mk;
-                else if (q >= MF16_NQG) P.s16_mk[par][MF16_NMG + q - MF16_NQG][lane] = mk;
-            };
-            for (int q = 0; q < MF16_NQG; q++) put(q, q < (int)G[lane].size() ? &G[lane][q] : nullptr);
-            for (int q = 0; q < MF16_NQB; q++) put(MF16_NQG + q, q < (int)B[lane].size() ? &B[lane][q] : nullptr);
-        }
-    }
-}
-
-// ------------------------------------------------------------------ parameter set (a10)
-void build_params(DevParams &P)
-{
-    memset(&P, 0, sizeof P);
-    for (int s = 0; s <= MF_MAX_SPAN + 1; s++) {
-        if (s <= 30) P.hairpinE[s] = T99_hairpin37[s];
-        else P.hairpinE[s] = T99_hairpin37[30] + (int)(T99_lxc37 * log(s / 30.));
-    }
-    for (int k = 0; k < 31; k++) { P.bulge[k] = T99_bulge37[k]; P.internal_loop[k] = T99_internal_loop37[k]; }
-    for (int k = 0; k < 64; k++) { P.stack[k] = T99_stack37[k]; P.pair[k] = (unsigned char)T99_BP_pair[k]; }
-    for (int k = 0; k < 200; k++) { P.mismatchI[k] = T99_mismatchI37[k]; P.mismatchH[k] = T99_mismatchH37[k]; }
-    for (int k = 0; k < 40; k++) {  // dangles are clamped to <= 0 by scale_parameters
-        P.dangle5[k] = std::min(0, T99_dangle5_37[k]);
-        P.dangle3[k] = std::min(0, T99_dangle3_37[k]);
-    }
-    for (int t = 0; t < 8; t++) {
-        P.MLintern[t] = T99_ML_intern37 + (t > 2 ? T99_TerminalAU : 0);
-        P.rtype[t] = (unsigned char)T99_rtype[t];
-    }
-    memcpy(P.int11, T99_int11_37, sizeof P.int11);
-    memcpy(P.int21, T99_int21_37, sizeof P.int21);
-    memcpy(P.int22, T99_int22_37, sizeof P.int22);
-    P.MLclosing = T99_ML_closing37;
-    P.TerminalAU = T99_TerminalAU;
-    // tetraloop bonus by packed 6-mer (first listed entry wins, like strstr)
-    for (int k = T99_N_TETRALOOPS - 1; k >= 0; k--) {
-        int code = 0;
-        bool ok = true;
-        for (int c = 0; c < 6; c++) {
-            const char ch = T99_Tetraloops[7 * k + c];
-            int b = ch == 'A' ? 0 : ch == 'C' ? 1 : ch == 'G' ? 2 : ch == 'U' ? 3 : -1;
-            if (b < 0) ok = false;
-            code |= (b & 3) << (2 * c);
-        }
-        if (ok) P.tetra[code] = (short)T99_TETRA_ENERGY37[k];
-    }
-    // generic interior-loop constants: iteration it pairs loop sizes s=it and s=30-it in one warp
-    const int ninio = T99_F_ninio37[2], maxninio = T99_MAX_NINIO;
-    for (int it = 0; it < 16; it++)
-        for (int lane = 0; lane < 32; lane++) {
-            int s, u;
-            if (it < 15) { if (lane <= it) { s = it; u = lane; } else { s = 30 - it; u = lane - it - 1; } }
-            else { s = 15; u = lane; }
-            const int v = s - u;
-            int val = MF_INF;
-            if (u >= 0 && v >= 0 && u <= s) {
-                const bool special = (u == 0 || v == 0 || (u <= 2 && v <= 2));
-                if (!special) val = T99_internal_loop37[s] + std::min(maxninio, std::abs(u - v) * ninio);
-            }
-            P.ilc[it][lane] = val;
-        }
-    // skewed-ring schedule: lane = bank class (u - A*(u+v)) mod 32, <= MF_GEN_ITERS terms per lane
+// result buffers shared by all devices of one mirfold_fold call
+struct SharedOut {
+    HBuf hits, arena;
+    uint64_t hits_cap = 0, arena_cap = 0;     // records / bytes
+    uint64_t hits_used = 0, arena_used = 0;
+    std::mutex mu;
+    std::vector<std::unique_ptr<OverflowChunk>> overflow;
+    uint64_t *hit_begin = nullptr;
+    uint32_t *hit_count = nullptr;
+    int32_t *totals = nullptr;
+    bool reserve(uint64_t nh, uint64_t ab, uint64_t &hb, uint64_t &abase)
     {
-        int fill[32] = {0};
-        for (int k = 0; k < MF_GEN_ITERS; k++)
-            for (int l = 0; l < 32; l++) { P.gen_c[k][l] = MF_INF; P.gen_us[k][l] = 0; }
-        for (int u = 0; u <= 30; u++)
-            for (int v = 0; u + v <= 30; v++) {
-                if (u == 0 || v == 0 || (u <= 2 && v <= 2)) continue;
-                const int cls = (((u - MF_SKEW_A * (u + v)) % 32) + 32) % 32;
-                const int k = fill[cls]++;
-                if (k >= MF_GEN_ITERS) { fprintf(stderr, "mirfold: skew schedule overflow\n"); abort(); }
-                P.gen_c[k][cls] = T99_internal_loop37[u + v] + std::min(maxninio, std::abs(u - v) * ninio);
-                P.gen_us[k][cls] = u | ((u + v) << 8) | (1 << 16);
-            }
+        std::lock_guard<std::mutex> lk(mu);
+        if (hits_used + nh > hits_cap || arena_used + ab > arena_cap) return false;
+        hb = hits_used; abase = arena_used;
+        hits_used += nh; arena_used += ab;
+        return true;
     }
-    int m = 0;
-    for (int u = 0; u <= 30; u++)
-        for (int v = 0; v <= 30 - u; v++) { P.uv[m][0] = (unsigned char)u; P.uv[m][1] = (unsigned char)v; m++; }
-    build_s16_schedule(P);
-}
+};
+
+enum { SINK_NONE = 0, SINK_SHARED = 1, SINK_STREAM = 2 };
+
+struct Job {   // one fold call; shared read-only by the device threads (sinks are synchronised)
+    const char *seqs = nullptr;
+    const uint64_t *h_off = nullptr;
+    int L = 0;
+    bool force_wide = false;
+    bool serial = false;               // MIRFOLD_FLAG_SERIAL: one lane
+    int sink = SINK_NONE;
+    SharedOut *shared = nullptr;
+    mirfold_chunk_fn fn = nullptr;
+    void *user = nullptr;
+    std::mutex *cb_mu = nullptr;
+    std::atomic<int> *cb_abort = nullptr;
+};
+
+struct DevOut {
+    mirfold_stats st{};
+    uint64_t nhits = 0, arena_bytes = 0;
+    int err = MIRFOLD_OK;
+    std::string errmsg;
+};
 
 // host-side phase log (MIRFOLD_HOST_TIMING=1): where the wall time outside the kernels goes
 struct HostTimer {
@@ -277,25 +250,57 @@ int env_opts()
     return v;
 }
 
-uint64_t cells_of(int n, int L)
-{   // sum_{i=1}^{n-4} (min(n, i+L*) - i - 3)
-    const int Ls = std::min(L, n);
-    uint64_t tot = 0;
+uint64_t cells_of(int64_t n, int L)
+{   // sum_{i=1}^{n-4} (min(n, i+L*) - i - 3); rows with i+L* <= n contribute L*-3, the rest n-i-3
     if (n < 5) return 0;
-    // rows with i+Ls <= n contribute Ls-3, the rest n-i-3
-    const int full = std::max(0, std::min(n - 4, n - Ls));
-    tot += (uint64_t)full * (uint64_t)(Ls - 3);
-    for (int i = full + 1; i <= n - 4; i++) tot += (uint64_t)(n - i - 3);
-    return tot;
+    const int64_t Ls = std::min<int64_t>(L, n);
+    const int64_t full = std::max<int64_t>(0, std::min(n - 4, n - Ls));
+    const int64_t m = n - 4 - full;
+    return (uint64_t)(full * (Ls - 3) + m * (m + 1) / 2);
+}
+
+// ---- shard plan: records in descending DP cells (== descending length for a fixed span, ties by
+// record index), greedy longest-processing-time assignment.  Every shard list stays in that order, which is
+// also the order the device's CTA scheduler wants (largest first).
+void plan_shards(const uint64_t *off, uint32_t nseq, int L, int G, std::vector<std::vector<uint32_t>> &shard, std::vector<uint64_t> &load)
+{
+    shard.assign((size_t)G, {});
+    load.assign((size_t)G, 0);
+    if (nseq == 0) return;
+    std::vector<uint32_t> order(nseq);
+    uint64_t maxn = 0;
+    for (uint32_t r = 0; r < nseq; r++) maxn = std::max(maxn, off[r + 1] - off[r]);
+    if (maxn <= 4ull * nseq + 65536) {   // counting sort by length, stable in the record index
+        std::vector<uint32_t> cnt((size_t)maxn + 2, 0);
+        for (uint32_t r = 0; r < nseq; r++) cnt[(size_t)(maxn - (off[r + 1] - off[r])) + 1]++;
+        for (size_t k = 1; k < cnt.size(); k++) cnt[k] += cnt[k - 1];
+        for (uint32_t r = 0; r < nseq; r++) order[cnt[(size_t)(maxn - (off[r + 1] - off[r]))]++] = r;
+    } else {
+        for (uint32_t r = 0; r < nseq; r++) order[r] = r;
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return off[a + 1] - off[a] > off[b + 1] - off[b]; });
+    }
+    if (G == 1) {
+        for (uint32_t r : order) load[0] += cells_of((int64_t)(off[r + 1] - off[r]), L) + 1;
+        shard[0].swap(order);
+        return;
+    }
+    for (auto &s : shard) s.reserve(nseq / G + 16);
+    for (uint32_t r : order) {
+        int g = 0;
+        for (int k = 1; k < G; k++) if (load[k] < load[g]) g = k;
+        shard[g].push_back(r);
+        load[g] += cells_of((int64_t)(off[r + 1] - off[r]), L) + 1;
+    }
 }
 
 #define CK(call)                                                                                 \
     do {                                                                                         \
         cudaError_t e_ = (call);                                                                 \
         if (e_ != cudaSuccess) {                                                                 \
-            out.err = MIRFOLD_ERR_CUDA;                                                          \
+            out.err = e_ == cudaErrorMemoryAllocation ? MIRFOLD_ERR_NOMEM : MIRFOLD_ERR_CUDA;    \
             out.errmsg = std::string(#call) + ": " + cudaGetErrorString(e_);                     \
-            return;                                                                              \
+            cudaGetLastError();                                                                  \
+            return false;                                                                        \
         }                                                                                        \
     } while (0)
 
@@ -315,34 +320,24 @@ __global__ void k_emit_sizes(const int *__restrict__ flag, const int *__restrict
         ones[k] = f ? 1ULL : 0ULL;
     }
 }
-
-__global__ void k_gather_bounds(const unsigned long long *tb_base, const unsigned long long *hitidx,
-                                unsigned long long *out, int nl)
+// per-locus first-hit index = hitidx[tb_base[l]] and total line F[seq_off + 1]
+__global__ void k_gather_bounds(const unsigned long long *tb_base, const unsigned long long *hitidx, const LocusDesc *loci,
+                                const int *F, unsigned long long *out, int *totals, int nl)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k <= nl) out[k] = hitidx[tb_base[k]];
-}
-__global__ void k_gather_totals(const LocusDesc *loci, const int *F, int *out, int nl)
-{
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < nl) out[k] = F[loci[k].seq_off + 1];
+    if (k < nl) totals[k] = F[loci[k].seq_off + 1];
 }
 
-cudaError_t exclusive_scan(Device &D, const unsigned long long *in, unsigned long long *out, size_t n)
+cudaError_t exclusive_scan(Lane &Ln, const unsigned long long *in, unsigned long long *out, size_t n, cudaStream_t st)
 {
     size_t tmp = 0;
-    cudaError_t e = cub::DeviceScan::ExclusiveSum(nullptr, tmp, in, out, n, D.stream);
+    cudaError_t e = cub::DeviceScan::ExclusiveSum(nullptr, tmp, in, out, n, st);
     if (e != cudaSuccess) return e;
-    e = D.scan_tmp.ensure(tmp);
+    e = Ln.scan_tmp.ensure(tmp);
     if (e != cudaSuccess) return e;
-    return cub::DeviceScan::ExclusiveSum(D.scan_tmp.p, tmp, in, out, n, D.stream);
+    return cub::DeviceScan::ExclusiveSum(Ln.scan_tmp.p, tmp, in, out, n, st);
 }
-
-struct Locus {
-    uint32_t rec;
-    int n;
-    uint64_t cells;
-};
 
 // Band shape of one locus: stride bucket or, for n > MF_TILE_LEN with a span that leaves at least
 // MF_TILE_MIN_STEP owned rows per tile, overlapping tiles for the shared-memory kernels.
@@ -407,285 +402,616 @@ unsigned long long build_fill_units(const LocusDesc *loci, int nl, std::vector<L
     return ring_acc;
 }
 
-// Runs the full pipeline for `recs` on one device.  If d_raw != nullptr the raw sequences already
-// live on the device (offsets h_off are into that buffer) and no results are downloaded.
-void run_device(Device &D, const char *seqs, const uint64_t *h_off, const std::vector<uint32_t> &recs, int L,
-                const char *d_raw, bool download, cudaStream_t user_stream, bool force_wide, Partial &out)
+// device bytes one locus needs on a lane: band (C, M, Mp), ring, descriptors, sequence-sized arrays and an
+// estimate of the per-traceback buffers (slots, stacks, per-traceback ints: about one traceback per 8 nt)
+size_t locus_bytes(int n, int L)
 {
-    out.st = mirfold_stats{};
-    out.st.n_devices = 1;
-    CK(cudaSetDevice(D.id));
-    cudaStream_t st = user_stream ? user_stream : D.stream;
-    const auto t0 = std::chrono::steady_clock::now();
+    LocusDesc d{};
+    const unsigned long long be = shape_locus(d, n, L);
+    const size_t per_tb = (size_t)((std::min(L, n) + 8) & ~3) + (size_t)(std::min(L, n) / 4 + 16) * 8 + 64;
+    return (size_t)be * 12 + (size_t)(d.tile_last + 1) * unit_ring_elems(std::min(n, d.tile_last ? MF_TILE_LEN : n), d.stride) * 4 +
+           (size_t)(d.tile_last + 2) * sizeof(LocusDesc) + (size_t)n * 16 + (size_t)(n / 8 + 2) * per_tb + 4096;
+}
 
-    std::vector<Locus> loci;
-    loci.reserve(recs.size());
-    for (uint32_t r : recs) {
-        const uint64_t len = h_off[r + 1] - h_off[r];
-        if (len >= 5) {
-            Locus l{r, (int)len, cells_of((int)len, L)};
-            loci.push_back(l);
-            out.st.nt += len;
-            out.st.cells += l.cells;
-        } else out.st.nt += len;
-    }
-    // largest first: the hardware CTA scheduler then behaves like LPT list scheduling
-    std::stable_sort(loci.begin(), loci.end(), [](const Locus &a, const Locus &b) { return a.cells > b.cells; });
-
-    out.recs.clear(); out.rec_hit_begin.clear(); out.rec_hit_count.clear(); out.rec_total.clear(); out.nhits = 0;
-    out.arena_bytes = 0;
-
-    HostTimer ht;
-    ht.mark("sort loci");
-    // ---- chunking by device memory budget
+// ------------------------------------------------------------------------------------------------------------
+// One device's share of a fold call.
+struct DevicePipeline {
+    Device &D;
+    const Job &J;
+    const char *d_raw;            // != nullptr: raw sequences already on this device
+    const uint64_t *raw_off;      // ... at these per-record offsets
+    DevOut &out;
+    std::vector<Locus> loci;      // descending DP cells
     struct Chunk { size_t begin, end; };
     std::vector<Chunk> chunks;
-    auto locus_bytes = [&](const Locus &l) {
-        LocusDesc d{};
-        const unsigned long long be = shape_locus(d, l.n, L);
-        return (size_t)be * 12 + (size_t)(d.tile_last + 1) * unit_ring_elems(std::min(l.n, d.tile_last ? MF_TILE_LEN : l.n), d.stride) * 4 +
-               (size_t)(d.tile_last + 2) * sizeof(LocusDesc) + (size_t)l.n * 16 + 4096;
-    };
+    HostTimer ht;
+
+    DevicePipeline(Device &D_, const Job &J_, const char *d_raw_, const uint64_t *raw_off_, DevOut &out_)
+        : D(D_), J(J_), d_raw(d_raw_), raw_off(raw_off_), out(out_) {}
+
+    bool run(const std::vector<uint32_t> &recs)
     {
+        out.st = mirfold_stats{};
+        out.st.n_devices = 1;
+        CK(cudaSetDevice(D.id));
+        const auto t0 = std::chrono::steady_clock::now();
+        loci.reserve(recs.size());
+        uint64_t total_cells = 0;
+        for (uint32_t r : recs) {
+            const uint64_t len = J.h_off[r + 1] - J.h_off[r];
+            out.st.nt += len;
+            if (len >= 5) {
+                Locus l{r, (int)len, cells_of((int64_t)len, J.L)};
+                loci.push_back(l);
+                total_cells += l.cells;
+            }
+        }
+        out.st.cells = total_cells;
+        plan_chunks(total_cells);
+        out.st.n_chunks = (int32_t)chunks.size();
+        ht.mark("plan chunks");
+        const int nlanes = (J.serial || chunks.size() < 2) ? 1 : 2;
+        bool ok = true;
+        if (!chunks.empty()) {
+            CK(cudaEventRecord(D.ev_first, D.lane[0].s_lo));
+            ok = front(D.lane[0], 0);
+            for (size_t k = 0; ok && k < chunks.size(); k++) {
+                Lane &Ln = D.lane[k % nlanes];
+                if (nlanes == 2 && k + 1 < chunks.size()) ok = front(D.lane[(k + 1) % 2], k + 1);   // its fill overlaps everything below
+                ok = ok && middle(Ln) && back(Ln, k + 1 == chunks.size());
+                if (nlanes == 1 && ok && k + 1 < chunks.size()) ok = front(Ln, k + 1);
+                if (J.cb_abort && J.cb_abort->load()) { out.err = MIRFOLD_ERR_CALLBACK; out.errmsg = "chunk callback returned non-zero"; ok = false; }
+            }
+            for (int l = 0; ok && l < nlanes; l++) ok = retire(D.lane[l]);
+        }
+        if (!ok) {   // nothing may stay in flight into buffers the caller is about to drop
+            cudaDeviceSynchronize();
+            cudaGetLastError();
+            D.lane[0].pending = D.lane[1].pending = false;
+            D.lane[0].ovf.reset(); D.lane[1].ovf.reset();
+            return false;
+        }
+        if (!chunks.empty()) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, D.ev_first, D.ev_last);
+            out.st.ms_device = ms;
+        }
+        out.st.ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        return true;
+    }
+
+    // chunks of about equal device bytes, each within a lane's budget; when results are downloaded a shard is cut
+    // into a few more chunks than memory demands so that downloads and host work overlap the next chunk's fill
+    void plan_chunks(uint64_t total_cells)
+    {
+        if (loci.empty()) return;
+        static const double cells_per_chunk = getenv("MIRFOLD_CHUNK_CELLS") ? atof(getenv("MIRFOLD_CHUNK_CELLS")) : 2.5e8;
+        std::vector<size_t> lb(loci.size());
+        size_t total = 0;
+        int last_n = -1; size_t last_b = 0;
+        for (size_t k = 0; k < loci.size(); k++) {
+            if (loci[k].n != last_n) { last_n = loci[k].n; last_b = locus_bytes(last_n, J.L); }
+            lb[k] = last_b; total += last_b;
+        }
+        const size_t lane_budget = std::max<size_t>(D.mem_budget / (J.serial ? 1 : 2), 1);
+        size_t nch = (total + lane_budget - 1) / lane_budget;
+        if (J.sink != SINK_NONE || nch > 1) nch = std::max<size_t>(nch, std::min<size_t>(64, (size_t)(total_cells / cells_per_chunk)));
+        nch = std::max<size_t>(nch, 1);
+        const size_t target = std::min(lane_budget, total / nch + 1);
         size_t b = 0, acc = 0;
         for (size_t k = 0; k < loci.size(); k++) {
-            const size_t lb = locus_bytes(loci[k]);
-            if (k > b && acc + lb > D.mem_budget) { chunks.push_back({b, k}); b = k; acc = 0; }
-            acc += lb;
+            if (k > b && acc + lb[k] > target) { chunks.push_back({b, k}); b = k; acc = 0; }
+            acc += lb[k];
         }
-        if (b < loci.size()) chunks.push_back({b, loci.size()});
+        chunks.push_back({b, loci.size()});
     }
-    out.st.n_chunks = (int32_t)chunks.size();
 
-    struct ChunkOut {  // device-resident results of a chunk, downloaded at the end
-        uint64_t nhits, arena_bytes;
-    };
-    // pass 1 over chunks computes everything and downloads the small per-hit arrays + arena
-    // into the pinned arena (grown as needed; chunks are few).
-    std::vector<char> arena_tmp;  // only used when more than one chunk
-    for (size_t ci = 0; ci < chunks.size(); ci++) {
-        const size_t cb = chunks[ci].begin, ce = chunks[ci].end;
-        const int nl = (int)(ce - cb);
-        // ---- descriptors
-        CK(D.h_loci.ensure(sizeof(LocusDesc) * nl));
-        CK(D.h_listoff.ensure(sizeof(unsigned long long) * nl));
-        LocusDesc *hl = D.h_loci.as<LocusDesc>();
-        unsigned long long *hlo = D.h_listoff.as<unsigned long long>();
-        unsigned long long seq_acc = 0, band_acc = 0, raw_acc = 0, list_acc = 0;
-        int max_n = 0, max_Ls = 0;
+    // ---- front: descriptors, upload, encode, band fill, f3, emission plan (everything up to the first host sync)
+    bool front(Lane &Ln, size_t ci)
+    {
+        if (!retire(Ln)) return false;
+        Prep &P = Ln.prep;
+        P = Prep{};
+        P.cb = chunks[ci].begin; P.ce = chunks[ci].end;
+        const int nl = P.nl = (int)(P.ce - P.cb);
+        CK(Ln.h_loci.ensure(sizeof(LocusDesc) * nl));
+        CK(Ln.h_listoff.ensure(sizeof(unsigned long long) * nl));
+        LocusDesc *hl = Ln.h_loci.as<LocusDesc>();
+        unsigned long long *hlo = Ln.h_listoff.as<unsigned long long>();
         for (int k = 0; k < nl; k++) {
-            const Locus &l = loci[cb + k];
+            const Locus &l = loci[P.cb + k];
             LocusDesc &d = hl[k];
             d = LocusDesc{};
-            const unsigned long long be = shape_locus(d, l.n, L);
+            const unsigned long long be = shape_locus(d, l.n, J.L);
             d.rec = (int)l.rec;
-            d.seq_off = seq_acc; d.band_off = band_acc; d.ring_off = 0;
-            d.raw_off = d_raw ? h_off[l.rec] : raw_acc;
-            hlo[k] = list_acc;
-            seq_acc += (unsigned long long)l.n + 3;
-            band_acc += be;
-            raw_acc += (unsigned long long)l.n;
-            list_acc += (unsigned long long)l.n / 2 + 2;
-            max_Ls = std::max(max_Ls, d.Ls);
+            d.seq_off = P.seq_acc; d.band_off = P.band_acc; d.ring_off = 0;
+            d.raw_off = d_raw ? raw_off[l.rec] : P.raw_acc;
+            hlo[k] = P.list_acc;
+            P.seq_acc += (unsigned long long)l.n + 3;
+            P.band_acc += be;
+            P.raw_acc += (unsigned long long)l.n;
+            P.list_acc += (unsigned long long)l.n / 2 + 2;
+            P.max_Ls = std::max(P.max_Ls, d.Ls);
         }
-        std::vector<LocusDesc> &units = D.units_host;
-        int bucket_first[5];
-        const unsigned long long ring_acc = build_fill_units(hl, nl, units, bucket_first, max_n);
-        const int nu = (int)units.size();
+        while (P.n_long < nl && hl[P.n_long].n > MF_TILE_LEN) P.n_long++;   // sorted by descending cells == descending n
+        std::vector<LocusDesc> units;
+        P.ring_acc = build_fill_units(hl, nl, units, P.bucket_first, P.max_n);
+        const int nu = P.nu = (int)units.size();
+        CK(Ln.h_units.ensure(sizeof(LocusDesc) * (size_t)nu + 64));
+        memcpy(Ln.h_units.p, units.data(), sizeof(LocusDesc) * (size_t)nu);
         out.st.fill_units += (uint64_t)nu;
-        ht.mark("descriptors + fill units");
+        // ---- buffers (grow-only; cudaFree of an outgrown buffer synchronises the device, which also orders it after its last use)
+        CK(Ln.loci.ensure(sizeof(LocusDesc) * nl));
+        CK(Ln.listoff.ensure(sizeof(unsigned long long) * nl));
+        CK(Ln.codes.ensure(P.seq_acc));
+        CK(Ln.F.ensure(P.seq_acc * 4));
+        CK(Ln.C.ensure(P.band_acc * 4));
+        CK(Ln.M.ensure(P.band_acc * 4));
+        if (!J.force_wide) CK(Ln.Mp.ensure(P.band_acc * 4));
+        CK(Ln.ring.ensure(P.ring_acc * 4));
+        CK(Ln.tbcount.ensure((size_t)nl * 4));
+        CK(Ln.tbbase.ensure((size_t)(nl + 1) * 8));
+        CK(Ln.scan_in.ensure((size_t)(nl + 1) * 8));
+        CK(Ln.startlist.ensure(P.list_acc * 4));
+        CK(Ln.fail.ensure(4));
+        CK(Ln.fillflags.ensure((size_t)nu * 4 + 4));
+        CK(Ln.units.ensure(sizeof(LocusDesc) * (size_t)nu + 64));
+        CK(Ln.h_small.ensure(256));
         // ---- upload
-        CK(cudaEventRecord(D.ev[0], st));
+        cudaStream_t lo = Ln.s_lo, hi = Ln.s_hi;
+        CK(cudaEventRecord(Ln.ev[0], lo));
         const char *raw_dev = d_raw;
         if (!d_raw) {
-            CK(D.h_raw.ensure(raw_acc));
-            char *hr = D.h_raw.as<char>();
-            for (int k = 0; k < nl; k++) memcpy(hr + hl[k].raw_off, seqs + h_off[loci[cb + k].rec], (size_t)hl[k].n);
-            CK(D.raw.ensure(raw_acc));
-            CK(cudaMemcpyAsync(D.raw.p, hr, raw_acc, cudaMemcpyHostToDevice, st));
-            out.st.h2d_bytes += raw_acc;
-            raw_dev = D.raw.as<char>();
+            CK(Ln.h_raw.ensure(P.raw_acc));
+            char *hr = Ln.h_raw.as<char>();
+            for (int k = 0; k < nl; k++) memcpy(hr + hl[k].raw_off, J.seqs + J.h_off[loci[P.cb + k].rec], (size_t)hl[k].n);
+            CK(Ln.raw.ensure(P.raw_acc));
+            CK(cudaMemcpyAsync(Ln.raw.p, hr, P.raw_acc, cudaMemcpyHostToDevice, lo));
+            out.st.h2d_bytes += P.raw_acc;
+            raw_dev = Ln.raw.as<char>();
         }
-        CK(D.loci.ensure(sizeof(LocusDesc) * nl));
-        CK(cudaMemcpyAsync(D.loci.p, hl, sizeof(LocusDesc) * nl, cudaMemcpyHostToDevice, st));
-        CK(D.listoff.ensure(sizeof(unsigned long long) * nl));
-        CK(cudaMemcpyAsync(D.listoff.p, hlo, sizeof(unsigned long long) * nl, cudaMemcpyHostToDevice, st));
-        out.st.h2d_bytes += (sizeof(LocusDesc) + 8) * (uint64_t)nl;
-        CK(D.codes.ensure(seq_acc));
-        CK(D.F.ensure(seq_acc * 4));
-        CK(D.C.ensure(band_acc * 4));
-        CK(D.M.ensure(band_acc * 4));
-        if (!force_wide) CK(D.Mp.ensure(band_acc * 4));
-        CK(D.ring.ensure(ring_acc * 4));
-        CK(D.tbcount.ensure((size_t)nl * 4));
-        CK(D.tbbase.ensure((size_t)(nl + 1) * 8));
-        CK(D.scan_in.ensure((size_t)(nl + 1) * 8));
-        CK(D.startlist.ensure(list_acc * 4));
-        CK(D.fail.ensure(4));
-        CK(cudaMemsetAsync(D.fail.p, 0, 4, st));
-        CK(D.fillflags.ensure((size_t)nu * 4 + 4));
-        CK(cudaMemsetAsync(D.fillflags.p, 0, (size_t)nu * 4 + 4, st));
-        CK(D.units.ensure(sizeof(LocusDesc) * (size_t)nu + 64));
-        CK(cudaMemcpyAsync(D.units.p, units.data(), sizeof(LocusDesc) * (size_t)nu, cudaMemcpyHostToDevice, st));
-        out.st.h2d_bytes += sizeof(LocusDesc) * (uint64_t)nu;
-        CK(cudaEventRecord(D.ev[1], st));
-        ht.mark("stage raw + enqueue uploads");
-        // ---- K1..K3
-        const LocusDesc *dl = D.loci.as<LocusDesc>();
-        CK(launch_prepare(raw_dev, dl, nl, seq_acc, D.codes.as<unsigned char>(), D.F.as<int>(), st));
-        CK(cudaEventRecord(D.ev[2], st));
-        FillLaunch fa{D.units.as<LocusDesc>(), nu, max_n, D.codes.as<unsigned char>(), D.C.as<int>(), D.M.as<int>(), D.ring.as<int>(),
-                      D.Mp.as<unsigned int>(), D.dP, {0, 0, 0, 0, 0}, D.fillflags.as<int>(), force_wide ? 1 : 0, env_opts()};
-        for (int b = 0; b < 5; b++) fa.bucket_first[b] = bucket_first[b];
+        CK(cudaMemcpyAsync(Ln.loci.p, hl, sizeof(LocusDesc) * nl, cudaMemcpyHostToDevice, lo));
+        CK(cudaMemcpyAsync(Ln.listoff.p, hlo, sizeof(unsigned long long) * nl, cudaMemcpyHostToDevice, lo));
+        CK(cudaMemcpyAsync(Ln.units.p, Ln.h_units.p, sizeof(LocusDesc) * (size_t)nu, cudaMemcpyHostToDevice, lo));
+        out.st.h2d_bytes += (sizeof(LocusDesc) + 8) * (uint64_t)nl + sizeof(LocusDesc) * (uint64_t)nu;
+        CK(cudaMemsetAsync(Ln.fail.p, 0, 4, lo));
+        CK(cudaMemsetAsync(Ln.fillflags.p, 0, (size_t)nu * 4 + 4, lo));
+        CK(cudaEventRecord(Ln.ev[1], lo));
+        // ---- K1, K2 on the low-priority stream
+        const LocusDesc *dl = Ln.loci.as<LocusDesc>();
+        CK(launch_prepare(raw_dev, dl, nl, P.seq_acc, Ln.codes.as<unsigned char>(), Ln.F.as<int>(), lo));
+        CK(cudaEventRecord(Ln.ev[2], lo));
+        FillLaunch fa{Ln.units.as<LocusDesc>(), nu, P.max_n, Ln.codes.as<unsigned char>(), Ln.C.as<int>(), Ln.M.as<int>(), Ln.ring.as<int>(),
+                      Ln.Mp.as<unsigned int>(), D.dP, {0, 0, 0, 0, 0}, Ln.fillflags.as<int>(), J.force_wide ? 1 : 0, env_opts()};
+        for (int b = 0; b < 5; b++) fa.bucket_first[b] = P.bucket_first[b];
         static const bool no_side = getenv("MIRFOLD_NO_SIDE_STREAM") != nullptr;   // A/B runs
-        CK(launch_fill(fa, st, no_side ? nullptr : D.side, D.ev[10], D.ev[11]));
-        CK(cudaEventRecord(D.ev[3], st));
-        int n_long = 0;
-        while (n_long < nl && hl[n_long].n > MF_TILE_LEN) n_long++;   // sorted by descending cells == descending n
-        CK(launch_f3(dl, nl, n_long, max_Ls, D.codes.as<unsigned char>(), D.C.as<int>(), D.F.as<int>(), D.dP, st));
+        CK(launch_fill(fa, lo, no_side ? nullptr : Ln.side, Ln.ev[10], Ln.ev[11]));
+        CK(cudaEventRecord(Ln.ev[3], lo));
+        // ---- K3 + emission plan on the high-priority stream
+        CK(cudaStreamWaitEvent(hi, Ln.ev[3], 0));
+        CK(launch_f3(dl, nl, P.n_long, P.max_Ls, Ln.codes.as<unsigned char>(), Ln.C.as<int>(), Ln.F.as<int>(), D.dP, hi));
         {   // kernels launched so far: k_prepare, the fill kernels (16-bit + 32-bit redo per non-empty bucket, generic), k_f3 / k_f3_cta
-            int nfill = bucket_first[1] > bucket_first[0] ? 1 : 0;
-            for (int b = 1; b < 4; b++) if (bucket_first[b + 1] > bucket_first[b]) nfill += force_wide ? 1 : 2;
-            out.st.kernel_launches += 1 + nfill + (n_long > 0 ? 1 : 0) + (n_long < nl ? 1 : 0);
+            int nfill = P.bucket_first[1] > P.bucket_first[0] ? 1 : 0;
+            for (int b = 1; b < 4; b++) if (P.bucket_first[b + 1] > P.bucket_first[b]) nfill += J.force_wide ? 1 : 2;
+            out.st.kernel_launches += 1 + nfill + (P.n_long > 0 ? 1 : 0) + (P.n_long < nl ? 1 : 0);
         }
-        CK(cudaEventRecord(D.ev[4], st));
-        // ---- K4: plan
-        TraceBuffers tb{};
-        tb.loci = dl; tb.nloci = nl; tb.codes = D.codes.as<unsigned char>();
-        tb.C = D.C.as<int>(); tb.M = D.M.as<int>(); tb.F = D.F.as<int>(); tb.P = D.dP;
-        tb.tb_count = D.tbcount.as<int>(); tb.tb_base = D.tbbase.as<unsigned long long>();
-        tb.list_off = D.listoff.as<unsigned long long>(); tb.tb_start_list = D.startlist.as<int>();
-        tb.fail_flag = D.fail.as<int>();
-        CK(launch_plan(tb, st));
-        k_widen_counts<<<(nl + 1 + 255) / 256, 256, 0, st>>>(tb.tb_count, D.scan_in.as<unsigned long long>(), nl);
+        CK(cudaEventRecord(Ln.ev[4], hi));
+        TraceBuffers &tb = Ln.tb;
+        tb = TraceBuffers{};
+        tb.loci = dl; tb.nloci = nl; tb.codes = Ln.codes.as<unsigned char>();
+        tb.C = Ln.C.as<int>(); tb.M = Ln.M.as<int>(); tb.F = Ln.F.as<int>(); tb.P = D.dP;
+        tb.tb_count = Ln.tbcount.as<int>(); tb.tb_base = Ln.tbbase.as<unsigned long long>();
+        tb.list_off = Ln.listoff.as<unsigned long long>(); tb.tb_start_list = Ln.startlist.as<int>();
+        tb.fail_flag = Ln.fail.as<int>();
+        CK(launch_plan(tb, hi));
+        k_widen_counts<<<(nl + 1 + 255) / 256, 256, 0, hi>>>(tb.tb_count, Ln.scan_in.as<unsigned long long>(), nl);
         CK(cudaGetLastError());
-        CK(exclusive_scan(D, D.scan_in.as<unsigned long long>(), tb.tb_base, (size_t)nl + 1));
-        CK(D.h_small.ensure(256));
-        unsigned long long *hs = D.h_small.as<unsigned long long>();
-        CK(cudaMemcpyAsync(&hs[0], tb.tb_base + nl, 8, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
+        CK(exclusive_scan(Ln, Ln.scan_in.as<unsigned long long>(), tb.tb_base, (size_t)nl + 1, hi));
+        CK(cudaMemcpyAsync(Ln.h_small.p, tb.tb_base + nl, 8, cudaMemcpyDeviceToHost, hi));
+        out.st.kernel_launches += 4;   // k_plan, k_widen_counts, cub scan (init + scan)
+        Ln.pending = true;
+        ht.mark("front (descriptors, uploads, K1-K3 enqueue)");
+        return true;
+    }
+
+    // ---- middle: tracebacks, emission decisions, output sizes (second host sync)
+    bool middle(Lane &Ln)
+    {
+        cudaStream_t hi = Ln.s_hi;
+        TraceBuffers &tb = Ln.tb;
+        const Prep &P = Ln.prep;
+        const int nl = P.nl;
+        unsigned long long *hs = Ln.h_small.as<unsigned long long>();
+        CK(cudaStreamSynchronize(hi));
         const unsigned long long ntb = hs[0];
         out.st.tracebacks += ntb;
-        out.st.kernel_launches += 4;   // k_plan, k_widen_counts, cub scan (init + scan)
-        ht.mark("K1-K3 enqueue + plan sync");
-        // ---- traceback
+        ht.mark("plan sync");
         tb.ntb = ntb;
-        tb.slot_stride = (max_Ls + 4 + 3) & ~3;
-        tb.stack_cap = max_Ls / 4 + 16;
-        tb.code_win = (max_Ls + 8 + 15) & ~15;
-        CK(D.slots.ensure((size_t)ntb * tb.slot_stride + 16));
-        CK(D.tblen.ensure((size_t)ntb * 4 + 16)); CK(D.tbstart.ensure((size_t)ntb * 4 + 16));
-        CK(D.tblocus.ensure((size_t)ntb * 4 + 16)); CK(D.tbflag.ensure((size_t)ntb * 4 + 16));
-        CK(D.tbenergy.ensure((size_t)ntb * 4 + 16));
-        CK(D.stackscr.ensure((size_t)ntb * tb.stack_cap * 8 + 16));
-        CK(D.ssoff.ensure((size_t)(ntb + 1) * 8)); CK(D.hitidx.ensure((size_t)(ntb + 1) * 8));
-        CK(D.scan_in.ensure((size_t)(ntb + 1) * 8 + (size_t)(nl + 1) * 8));
-        CK(D.scan_out.ensure((size_t)(ntb + 1) * 8));
-        tb.slots = D.slots.as<char>(); tb.tb_len = D.tblen.as<int>(); tb.tb_start = D.tbstart.as<int>();
-        tb.tb_locus = D.tblocus.as<int>(); tb.tb_flag = D.tbflag.as<int>(); tb.tb_energy = D.tbenergy.as<int>();
-        tb.stack_scratch = D.stackscr.as<int>();
-        CK(launch_traceback(tb, st));
-        CK(launch_emit(tb, st));
-        unsigned long long nhits = 0, abytes = 0;
+        tb.slot_stride = (P.max_Ls + 4 + 3) & ~3;
+        tb.stack_cap = P.max_Ls / 4 + 16;
+        tb.code_win = (P.max_Ls + 8 + 15) & ~15;
+        CK(Ln.slots.ensure((size_t)ntb * tb.slot_stride + 16));
+        CK(Ln.tblen.ensure((size_t)ntb * 4 + 16)); CK(Ln.tbstart.ensure((size_t)ntb * 4 + 16));
+        CK(Ln.tblocus.ensure((size_t)ntb * 4 + 16)); CK(Ln.tbflag.ensure((size_t)ntb * 4 + 16));
+        CK(Ln.tbenergy.ensure((size_t)ntb * 4 + 16));
+        CK(Ln.stackscr.ensure((size_t)ntb * tb.stack_cap * 8 + 16));
+        CK(Ln.ssoff.ensure((size_t)(ntb + 1) * 8)); CK(Ln.hitidx.ensure((size_t)(ntb + 1) * 8));
+        CK(Ln.scan_in.ensure((size_t)(ntb + 1) * 8 + (size_t)(nl + 1) * 8));
+        CK(Ln.scan_out.ensure((size_t)(ntb + 1) * 8));
+        tb.slots = Ln.slots.as<char>(); tb.tb_len = Ln.tblen.as<int>(); tb.tb_start = Ln.tbstart.as<int>();
+        tb.tb_locus = Ln.tblocus.as<int>(); tb.tb_flag = Ln.tbflag.as<int>(); tb.tb_energy = Ln.tbenergy.as<int>();
+        tb.stack_scratch = Ln.stackscr.as<int>();
+        CK(launch_traceback(tb, hi));
+        CK(launch_emit(tb, hi));
         if (ntb) {
-            k_emit_sizes<<<(unsigned)((ntb + 1 + 255) / 256), 256, 0, st>>>(tb.tb_flag, tb.tb_len, D.scan_in.as<unsigned long long>(),
-                                                                             D.scan_out.as<unsigned long long>(), ntb);
+            k_emit_sizes<<<(unsigned)((ntb + 1 + 255) / 256), 256, 0, hi>>>(tb.tb_flag, tb.tb_len, Ln.scan_in.as<unsigned long long>(),
+                                                                             Ln.scan_out.as<unsigned long long>(), ntb);
             CK(cudaGetLastError());
-            CK(exclusive_scan(D, D.scan_in.as<unsigned long long>(), D.ssoff.as<unsigned long long>(), (size_t)ntb + 1));
-            CK(exclusive_scan(D, D.scan_out.as<unsigned long long>(), D.hitidx.as<unsigned long long>(), (size_t)ntb + 1));
-            CK(cudaMemcpyAsync(&hs[1], D.ssoff.as<unsigned long long>() + ntb, 8, cudaMemcpyDeviceToHost, st));
-            CK(cudaMemcpyAsync(&hs[2], D.hitidx.as<unsigned long long>() + ntb, 8, cudaMemcpyDeviceToHost, st));
+            CK(exclusive_scan(Ln, Ln.scan_in.as<unsigned long long>(), Ln.ssoff.as<unsigned long long>(), (size_t)ntb + 1, hi));
+            CK(exclusive_scan(Ln, Ln.scan_out.as<unsigned long long>(), Ln.hitidx.as<unsigned long long>(), (size_t)ntb + 1, hi));
+            CK(cudaMemcpyAsync(&hs[1], Ln.ssoff.as<unsigned long long>() + ntb, 8, cudaMemcpyDeviceToHost, hi));
+            CK(cudaMemcpyAsync(&hs[2], Ln.hitidx.as<unsigned long long>() + ntb, 8, cudaMemcpyDeviceToHost, hi));
             out.st.kernel_launches += 7;
         }
-        CK(cudaMemcpyAsync(&hs[3], D.fail.p, 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        if (*(int *)&hs[3]) { out.err = MIRFOLD_ERR_BACKTRACK; out.errmsg = "traceback found no decomposition"; return; }
-        if (ntb) { abytes = hs[1]; nhits = hs[2]; }
-        CK(D.o_hits.ensure(nhits * sizeof(mirfold_hit) + 16)); CK(D.o_arena.ensure(abytes + 16));
-        CK(launch_pack(tb, D.ssoff.as<unsigned long long>(), D.hitidx.as<unsigned long long>(), D.o_arena.as<char>(),
-                       D.o_hits.as<mirfold_hit>(), out.arena_bytes, st));
-        out.st.kernel_launches += 1;
-        CK(cudaEventRecord(D.ev[5], st));
-        ht.mark("traceback..pack (sync inside)");
-        // ---- download
-        if (download) {
-            // per-locus first-hit index = hitidx[tb_base[l]] -> gather on host from two small arrays
-            CK(D.h_out.ensure((size_t)(nl + 1) * 8 + (size_t)nl * 4 + 64));
-            unsigned long long *h_tbbase = D.h_out.as<unsigned long long>();
-            int *h_total = (int *)(h_tbbase + nl + 1);
-            // hit table: the device wrote finished mirfold_hit records (ss_off already includes this chunk's
-            // arena base); they land in the pinned table the result will own -- no per-hit host work
-            const uint64_t hbase = out.nhits;
-            if (out.hits.cap < (hbase + nhits) * sizeof(mirfold_hit) + 16) {
-                HBuf bigger;
-                CK(bigger.ensure((hbase + nhits) * sizeof(mirfold_hit) * (hbase ? 2 : 1) + 16));
-                if (hbase) memcpy(bigger.p, out.hits.p, hbase * sizeof(mirfold_hit));
-                out.hits.release();
-                out.hits = bigger;
-            }
-            if (nhits)
-                CK(cudaMemcpyAsync(out.hits.as<mirfold_hit>() + hbase, D.o_hits.p, nhits * sizeof(mirfold_hit), cudaMemcpyDeviceToHost, st));
-            // hit index at each locus boundary: hitidx[tb_base[l]] (device gather -> reuse scan_in)
-            {
-                k_gather_bounds<<<(nl + 1 + 255) / 256, 256, 0, st>>>(tb.tb_base, D.hitidx.as<unsigned long long>(),
-                                                                      D.scan_in.as<unsigned long long>(), nl);
-                CK(cudaGetLastError());
-                out.st.kernel_launches += 1;
-                CK(cudaMemcpyAsync(h_tbbase, D.scan_in.p, (size_t)(nl + 1) * 8, cudaMemcpyDeviceToHost, st));
-            }
-            // totals: F[seq_off + 1] per locus -> strided; copy via 2D memcpy is awkward, use gather kernel
-            {
-                CK(D.tbcount.ensure((size_t)nl * 4));
-                k_gather_totals<<<(nl + 255) / 256, 256, 0, st>>>(dl, D.F.as<int>(), D.tbcount.as<int>(), nl);
-                CK(cudaGetLastError());
-                out.st.kernel_launches += 1;
-                CK(cudaMemcpyAsync(h_total, D.tbcount.p, (size_t)nl * 4, cudaMemcpyDeviceToHost, st));
-            }
-            // arena: straight into the pinned result arena
-            const uint64_t abase = out.arena_bytes;
-            if (chunks.size() == 1) {
-                CK(out.arena.ensure(abytes + 16));
-            } else {
-                // multi-chunk: grow by reallocating pinned memory (rare path)
-                if (out.arena.cap < abase + abytes + 16) {
-                    HBuf bigger;
-                    CK(bigger.ensure((abase + abytes) * 2 + 16));
-                    if (abase) memcpy(bigger.p, out.arena.p, abase);
-                    out.arena.release();
-                    out.arena = bigger;
-                }
-            }
-            if (abytes) CK(cudaMemcpyAsync(out.arena.as<char>() + abase, D.o_arena.p, abytes, cudaMemcpyDeviceToHost, st));
-            CK(cudaEventRecord(D.ev[6], st));
-            CK(cudaStreamSynchronize(st));
-            out.st.d2h_bytes += nhits * sizeof(mirfold_hit) + (uint64_t)(nl + 1) * 8 + (uint64_t)nl * 4 + abytes + 32;
-            ht.mark("download + sync");
-            out.nhits = hbase + nhits;
-            for (int k = 0; k < nl; k++) {
-                out.recs.push_back(loci[cb + k].rec);
-                out.rec_hit_begin.push_back(hbase + h_tbbase[k]);
-                out.rec_hit_count.push_back((uint32_t)(h_tbbase[k + 1] - h_tbbase[k]));
-                out.rec_total.push_back(h_total[k]);
-            }
-            out.arena_bytes = abase + abytes;
-            ht.mark("hit records");
-        } else {
-            CK(cudaEventRecord(D.ev[6], st));
-            CK(cudaStreamSynchronize(st));
-            out.arena_bytes += abytes;
-            out.st.d2h_bytes += 32;
-            // count only
-            out.rec_hit_begin.push_back(nhits);
-        }
-        float ms = 0;
-        cudaEventElapsedTime(&ms, D.ev[0], D.ev[1]); out.st.ms_h2d += ms;
-        cudaEventElapsedTime(&ms, D.ev[2], D.ev[3]); out.st.ms_fill += ms;
-        cudaEventElapsedTime(&ms, D.ev[3], D.ev[4]); out.st.ms_f3 += ms;
-        cudaEventElapsedTime(&ms, D.ev[4], D.ev[5]); out.st.ms_trace += ms;
-        cudaEventElapsedTime(&ms, D.ev[5], D.ev[6]); out.st.ms_d2h += ms;
-        cudaEventElapsedTime(&ms, D.ev[1], D.ev[5]); out.st.ms_device += ms;
+        CK(cudaMemcpyAsync(&hs[3], Ln.fail.p, 4, cudaMemcpyDeviceToHost, hi));
+        CK(cudaStreamSynchronize(hi));
+        if (*(int *)&hs[3]) { out.err = MIRFOLD_ERR_BACKTRACK; out.errmsg = "traceback found no decomposition"; return false; }
+        Ln.abytes = ntb ? hs[1] : 0;
+        Ln.nhits = ntb ? hs[2] : 0;
+        ht.mark("traceback sync");
+        return true;
     }
-    out.st.ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+
+    // ---- back: pack the printed structures and start the download into the sink (asynchronous; see retire)
+    bool back(Lane &Ln, bool last_chunk)
+    {
+        cudaStream_t hi = Ln.s_hi;
+        TraceBuffers &tb = Ln.tb;
+        const Prep &P = Ln.prep;
+        const int nl = P.nl;
+        const uint64_t nhits = Ln.nhits, abytes = Ln.abytes;
+        mirfold_hit *dst_hits = nullptr;
+        char *dst_arena = nullptr;
+        Ln.hit_base = Ln.arena_base = 0;
+        if (J.sink == SINK_SHARED) {
+            if (J.shared->reserve(nhits, abytes, Ln.hit_base, Ln.arena_base)) {
+                dst_hits = J.shared->hits.as<mirfold_hit>() + Ln.hit_base;
+                dst_arena = J.shared->arena.as<char>() + Ln.arena_base;
+            } else {
+                Ln.ovf.reset(new OverflowChunk());
+                CK(Ln.ovf->hits.ensure(nhits * sizeof(mirfold_hit) + 16));
+                CK(Ln.ovf->arena.ensure(abytes + 16));
+                Ln.ovf->nhits = nhits; Ln.ovf->abytes = abytes;
+                dst_hits = Ln.ovf->hits.as<mirfold_hit>();
+                dst_arena = Ln.ovf->arena.as<char>();
+            }
+        } else if (J.sink == SINK_STREAM) {
+            CK(Ln.h_hits.ensure(nhits * sizeof(mirfold_hit) + 16));
+            CK(Ln.h_arena.ensure(abytes + 16));
+            dst_hits = Ln.h_hits.as<mirfold_hit>();
+            dst_arena = Ln.h_arena.as<char>();
+        }
+        CK(Ln.o_hits.ensure(nhits * sizeof(mirfold_hit) + 16));
+        CK(Ln.o_arena.ensure(abytes + 16));
+        CK(Ln.bounds.ensure((size_t)(nl + 1) * 8));
+        CK(Ln.totals.ensure((size_t)nl * 4 + 4));
+        CK(launch_pack(tb, Ln.ssoff.as<unsigned long long>(), Ln.hitidx.as<unsigned long long>(), Ln.o_arena.as<char>(),
+                       Ln.o_hits.as<mirfold_hit>(), Ln.arena_base, hi));
+        out.st.kernel_launches += 1;
+        CK(cudaEventRecord(Ln.ev[5], hi));
+        if (last_chunk) CK(cudaEventRecord(D.ev_last, hi));
+        if (J.sink != SINK_NONE) {
+            if (tb.ntb) {
+                k_gather_bounds<<<(nl + 1 + 255) / 256, 256, 0, hi>>>(tb.tb_base, Ln.hitidx.as<unsigned long long>(), tb.loci, tb.F,
+                                                                      Ln.bounds.as<unsigned long long>(), Ln.totals.as<int>(), nl);
+                CK(cudaGetLastError());
+                out.st.kernel_launches += 1;
+            } else {
+                CK(cudaMemsetAsync(Ln.bounds.p, 0, (size_t)(nl + 1) * 8, hi));
+                CK(cudaMemsetAsync(Ln.totals.p, 0, (size_t)nl * 4, hi));
+            }
+            CK(Ln.h_out.ensure((size_t)(nl + 1) * 8 + (size_t)nl * 4 + 64));
+            unsigned long long *h_bounds = Ln.h_out.as<unsigned long long>();
+            int *h_total = (int *)(h_bounds + nl + 1);
+            if (nhits) CK(cudaMemcpyAsync(dst_hits, Ln.o_hits.p, nhits * sizeof(mirfold_hit), cudaMemcpyDeviceToHost, hi));
+            if (abytes) CK(cudaMemcpyAsync(dst_arena, Ln.o_arena.p, abytes, cudaMemcpyDeviceToHost, hi));
+            CK(cudaMemcpyAsync(h_bounds, Ln.bounds.p, (size_t)(nl + 1) * 8, cudaMemcpyDeviceToHost, hi));
+            CK(cudaMemcpyAsync(h_total, Ln.totals.p, (size_t)nl * 4, cudaMemcpyDeviceToHost, hi));
+            out.st.d2h_bytes += nhits * sizeof(mirfold_hit) + (uint64_t)(nl + 1) * 8 + (uint64_t)nl * 4 + abytes + 32;
+        } else out.st.d2h_bytes += 32;
+        CK(cudaEventRecord(Ln.ev[6], hi));
+        // the lane's next chunk (uploads on s_lo) may only start once this one has left the device
+        CK(cudaStreamWaitEvent(Ln.s_lo, Ln.ev[6], 0));
+        out.nhits += nhits;
+        out.arena_bytes += abytes;
+        ht.mark("back (pack + download enqueue)");
+        return true;
+    }
+
+    // ---- retire: wait for the lane's download, publish the chunk's per-record tables, collect stage times
+    bool retire(Lane &Ln)
+    {
+        if (!Ln.pending) return true;
+        Ln.pending = false;
+        CK(cudaEventSynchronize(Ln.ev[6]));
+        const Prep &P = Ln.prep;
+        const int nl = P.nl;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, Ln.ev[0], Ln.ev[1]); out.st.ms_h2d += ms;
+        cudaEventElapsedTime(&ms, Ln.ev[2], Ln.ev[3]); out.st.ms_fill += ms;
+        cudaEventElapsedTime(&ms, Ln.ev[3], Ln.ev[4]); out.st.ms_f3 += ms;
+        cudaEventElapsedTime(&ms, Ln.ev[4], Ln.ev[5]); out.st.ms_trace += ms;
+        cudaEventElapsedTime(&ms, Ln.ev[5], Ln.ev[6]); out.st.ms_d2h += ms;
+        if (J.sink == SINK_NONE) return true;
+        const unsigned long long *h_bounds = Ln.h_out.as<unsigned long long>();
+        const int *h_total = (const int *)(h_bounds + nl + 1);
+        if (J.sink == SINK_SHARED) {
+            SharedOut &S = *J.shared;
+            if (!Ln.ovf) {
+                for (int k = 0; k < nl; k++) {
+                    const uint32_t r = loci[P.cb + k].rec;
+                    S.hit_begin[r] = Ln.hit_base + h_bounds[k];
+                    S.hit_count[r] = (uint32_t)(h_bounds[k + 1] - h_bounds[k]);
+                    S.totals[r] = h_total[k];
+                }
+            } else {
+                OverflowChunk &O = *Ln.ovf;
+                O.recs.resize(nl); O.begin.resize(nl); O.count.resize(nl);
+                for (int k = 0; k < nl; k++) {
+                    const uint32_t r = loci[P.cb + k].rec;
+                    O.recs[k] = r; O.begin[k] = h_bounds[k]; O.count[k] = (uint32_t)(h_bounds[k + 1] - h_bounds[k]);
+                    S.totals[r] = h_total[k];
+                }
+                std::lock_guard<std::mutex> lk(S.mu);
+                S.overflow.push_back(std::move(Ln.ovf));
+            }
+        } else {
+            Ln.s_rec.resize(nl); Ln.s_begin.resize(nl); Ln.s_count.resize(nl); Ln.s_total.resize(nl);
+            for (int k = 0; k < nl; k++) {
+                Ln.s_rec[k] = loci[P.cb + k].rec;
+                Ln.s_begin[k] = h_bounds[k];
+                Ln.s_count[k] = (uint32_t)(h_bounds[k + 1] - h_bounds[k]);
+                Ln.s_total[k] = h_total[k];
+            }
+            mirfold_chunk c{};
+            c.n_records = (uint32_t)nl; c.device = D.id;
+            c.record = Ln.s_rec.data(); c.hit_begin = Ln.s_begin.data(); c.hit_count = Ln.s_count.data();
+            c.total_mfe_dcal = Ln.s_total.data();
+            c.nhits = Ln.nhits; c.hits = Ln.h_hits.as<mirfold_hit>();
+            c.ss_arena = Ln.h_arena.as<char>(); c.ss_bytes = Ln.abytes;
+            std::lock_guard<std::mutex> lk(*J.cb_mu);
+            if (!J.cb_abort->load() && J.fn(J.user, &c) != 0) J.cb_abort->store(1);
+        }
+        ht.mark("retire (download wait + record tables)");
+        return true;
+    }
+};
+#undef CK
+
+bool run_device(Device &D, const Job &J, const std::vector<uint32_t> &recs, const char *d_raw, const uint64_t *raw_off, DevOut &out)
+{
+    DevicePipeline p(D, J, d_raw, raw_off, out);
+    return p.run(recs);
+}
+
+HBuf pool_take(mirfold_ctx *ctx, std::vector<HBuf> &pool, size_t bytes)
+{   // smallest pooled buffer that is large enough, else the largest one (it will be re-grown by the caller)
+    std::lock_guard<std::mutex> lk(ctx->pool_mu);
+    int best = -1;
+    for (int k = 0; k < (int)pool.size(); k++)
+        if (pool[k].cap >= bytes && (best < 0 || pool[k].cap < pool[best].cap)) best = k;
+    HBuf b;
+    if (best >= 0) { b = pool[best]; pool.erase(pool.begin() + best); }
+    return b;
+}
+void pool_give(mirfold_ctx *ctx, std::vector<HBuf> &pool, HBuf &b)
+{   // caller holds ctx->pool_mu
+    if (!b.p) return;
+    if (ctx->closed) { b.release(); return; }
+    if (pool.size() >= 4) {
+        int small = 0;
+        for (int k = 1; k < (int)pool.size(); k++) if (pool[k].cap < pool[small].cap) small = k;
+        if (pool[small].cap < b.cap) std::swap(pool[small], b);
+        b.release();
+        return;
+    }
+    pool.push_back(b);
+    b = HBuf();
+}
+
+void add_stats(mirfold_stats &a, const mirfold_stats &b)
+{
+    a.ms_h2d = std::max(a.ms_h2d, b.ms_h2d); a.ms_fill = std::max(a.ms_fill, b.ms_fill);
+    a.ms_f3 = std::max(a.ms_f3, b.ms_f3); a.ms_trace = std::max(a.ms_trace, b.ms_trace);
+    a.ms_d2h = std::max(a.ms_d2h, b.ms_d2h); a.ms_device = std::max(a.ms_device, b.ms_device);
+    a.nt += b.nt; a.cells += b.cells; a.tracebacks += b.tracebacks; a.kernel_launches += b.kernel_launches;
+    a.h2d_bytes += b.h2d_bytes; a.d2h_bytes += b.d2h_bytes; a.n_chunks += b.n_chunks; a.fill_units += b.fill_units;
+}
+
+int validate_offsets(mirfold_ctx *ctx, const uint64_t *seq_off, uint32_t nseq)
+{
+    for (uint32_t r = 0; r < nseq; r++) {
+        if (seq_off[r + 1] < seq_off[r]) { ctx->last_error = "seq_off is not non-decreasing"; return MIRFOLD_ERR_ARG; }
+        if (seq_off[r + 1] - seq_off[r] > (uint64_t)0x3fffffff) { ctx->last_error = "a sequence is longer than 2^30 - 1 nt"; return MIRFOLD_ERR_ARG; }
+    }
+    return MIRFOLD_OK;
+}
+
+// the common engine behind mirfold_fold / mirfold_fold_stream / mirfold_fold_device / mirfold_batch_fold
+struct FoldArgs {
+    const char *seqs = nullptr;
+    const uint64_t *seq_off = nullptr;
+    uint32_t nseq = 0;
+    int span_L = 0;
+    uint32_t flags = 0;
+    int sink = SINK_SHARED;
+    mirfold_chunk_fn fn = nullptr;
+    void *user = nullptr;
+    // device-resident input: per device a buffer and per record its offset; `shard` then comes from the batch
+    const std::vector<void *> *d_raw = nullptr;
+    const uint64_t *raw_off = nullptr;
+    const std::vector<std::vector<uint32_t>> *shard = nullptr;
+    int n_devices = 0;   // 0 = all devices of the context
+};
+
+int fold_engine(mirfold_ctx *ctx, const FoldArgs &A, mirfold_result **out, mirfold_stats *stats_out)
+{
+    static const bool env_wide = getenv("MIRFOLD_FORCE_WIDE") != nullptr;   // A/B runs of bench.py
+    static const bool env_serial = getenv("MIRFOLD_SERIAL") != nullptr;
+    if (!ctx || !A.seq_off || (!A.seqs && !A.d_raw && A.nseq)) return MIRFOLD_ERR_ARG;
+    if (ctx->closed) return MIRFOLD_ERR_ARG;
+    if (A.span_L < 5 || A.span_L > MF_MAX_SPAN) { ctx->last_error = "span_L out of range [5, 4096]"; return MIRFOLD_ERR_ARG; }
+    if (out) *out = nullptr;
+    int rc = validate_offsets(ctx, A.seq_off, A.nseq);
+    if (rc != MIRFOLD_OK) return rc;
+    const auto t0 = std::chrono::steady_clock::now();
+    HostTimer ht;
+    const int G = A.n_devices > 0 ? A.n_devices : (int)ctx->devs.size();
+    const uint32_t nseq = A.nseq;
+    std::vector<std::vector<uint32_t>> shard_local;
+    std::vector<uint64_t> load;
+    if (!A.shard) plan_shards(A.seq_off, nseq, A.span_L, G, shard_local, load);
+    const std::vector<std::vector<uint32_t>> &shard = A.shard ? *A.shard : shard_local;
+    ht.mark("shard plan");
+
+    Job J;
+    J.seqs = A.seqs; J.h_off = A.seq_off; J.L = A.span_L;
+    J.force_wide = (A.flags & MIRFOLD_FLAG_WIDE) != 0 || env_wide || A.span_L > MF16_MAX_SPAN;
+    J.serial = (A.flags & MIRFOLD_FLAG_SERIAL) != 0 || env_serial;
+    J.sink = A.sink;
+    std::mutex cb_mu;
+    std::atomic<int> cb_abort{0};
+    J.fn = A.fn; J.user = A.user; J.cb_mu = &cb_mu; J.cb_abort = &cb_abort;
+
+    std::unique_ptr<ResultOwner> R;
+    SharedOut S;
+    const uint64_t nt_total = nseq ? A.seq_off[nseq] - A.seq_off[0] : 0;
+    if (A.sink != SINK_STREAM) {
+        R.reset(new ResultOwner());
+        R->ctx = ctx;
+        R->hit_begin.assign((size_t)nseq + 1, 0);
+        R->hit_count.assign((size_t)nseq + 1, 0);
+        R->totals.assign((size_t)nseq + 1, 0);
+    }
+    if (A.sink == SINK_SHARED) {
+        // capacity is an estimate (a chunk that does not fit takes the overflow path below); MIRFOLD_RESULT_CAP_SCALE
+        // shrinks it so that tests can reach that path
+        const char *cs = getenv("MIRFOLD_RESULT_CAP_SCALE");
+        const double scale = cs ? atof(cs) : 1.25;
+        S.hits_cap = (uint64_t)(ctx->hits_per_nt * scale * (double)nt_total) + (cs ? 1 : 4096);
+        S.arena_cap = (uint64_t)(ctx->arena_per_nt * scale * (double)nt_total) + (cs ? 1 : 65536);
+        S.hits = pool_take(ctx, ctx->hits_pool, S.hits_cap * sizeof(mirfold_hit));
+        S.arena = pool_take(ctx, ctx->arena_pool, S.arena_cap);
+        cudaSetDevice(ctx->devs[0].id);
+        if (S.hits.ensure(S.hits_cap * sizeof(mirfold_hit)) != cudaSuccess || S.arena.ensure(S.arena_cap) != cudaSuccess) {
+            cudaGetLastError();
+            S.hits.release(); S.arena.release();
+            ctx->last_error = "pinned result buffers";
+            return MIRFOLD_ERR_NOMEM;
+        }
+        if (!cs) { S.hits_cap = S.hits.cap / sizeof(mirfold_hit); S.arena_cap = S.arena.cap; }
+        S.hit_begin = R->hit_begin.data(); S.hit_count = R->hit_count.data(); S.totals = R->totals.data();
+        J.shared = &S;
+    }
+    ht.mark("result buffers");
+
+    std::vector<DevOut> parts(G);
+    auto dev_raw = [&](int g) { return A.d_raw ? (const char *)(*A.d_raw)[g] : nullptr; };
+    if (G == 1) run_device(ctx->devs[0], J, shard[0], dev_raw(0), A.raw_off, parts[0]);
+    else {
+        std::vector<std::thread> th;
+        for (int g = 0; g < G; g++)
+            th.emplace_back([&, g] { run_device(ctx->devs[g], J, shard[g], dev_raw(g), A.raw_off, parts[g]); });
+        for (auto &t : th) t.join();
+    }
+    for (int g = 0; g < G; g++)
+        if (parts[g].err != MIRFOLD_OK) {
+            ctx->last_error = parts[g].errmsg;
+            std::lock_guard<std::mutex> lk(ctx->pool_mu);
+            pool_give(ctx, ctx->hits_pool, S.hits);
+            pool_give(ctx, ctx->arena_pool, S.arena);
+            return parts[g].err;
+        }
+    ht.mark("devices");
+    mirfold_stats st{};
+    uint64_t nhits = 0, abytes = 0;
+    for (int g = 0; g < G; g++) { add_stats(st, parts[g].st); nhits += parts[g].nhits; abytes += parts[g].arena_bytes; }
+    st.n_devices = G;
+
+    if (A.sink == SINK_STREAM) {
+        // records without a DP band (shorter than 5 nt) were never part of a device chunk
+        std::vector<uint32_t> rec;
+        for (uint32_t r = 0; r < nseq; r++) if (A.seq_off[r + 1] - A.seq_off[r] < 5) rec.push_back(r);
+        if (!rec.empty()) {
+            std::vector<uint64_t> hb(rec.size(), 0);
+            std::vector<uint32_t> hc(rec.size(), 0);
+            std::vector<int32_t> tot(rec.size(), 0);
+            mirfold_chunk c{};
+            c.n_records = (uint32_t)rec.size(); c.device = -1;
+            c.record = rec.data(); c.hit_begin = hb.data(); c.hit_count = hc.data(); c.total_mfe_dcal = tot.data();
+            if (A.fn(A.user, &c) != 0) { ctx->last_error = "chunk callback returned non-zero"; return MIRFOLD_ERR_CALLBACK; }
+        }
+        st.ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        if (stats_out) *stats_out = st;
+        return MIRFOLD_OK;
+    }
+
+    if (A.sink == SINK_SHARED) {
+        if (!S.overflow.empty()) {
+            // the capacity estimate was too small: one exact-size copy, and a better estimate for the next call
+            uint64_t th = S.hits_used, ta = S.arena_used;
+            for (auto &o : S.overflow) { th += o->nhits; ta += o->abytes; }
+            HBuf nh, na;
+            if (nh.ensure(th * sizeof(mirfold_hit) + 16) != cudaSuccess || na.ensure(ta + 16) != cudaSuccess) {
+                cudaGetLastError();
+                nh.release(); na.release(); S.hits.release(); S.arena.release();
+                return MIRFOLD_ERR_NOMEM;
+            }
+            memcpy(nh.p, S.hits.p, S.hits_used * sizeof(mirfold_hit));
+            memcpy(na.p, S.arena.p, S.arena_used);
+            uint64_t hb = S.hits_used, ab = S.arena_used;
+            for (auto &o : S.overflow) {
+                mirfold_hit *dst = nh.as<mirfold_hit>() + hb;
+                memcpy(dst, o->hits.p, o->nhits * sizeof(mirfold_hit));
+                for (uint64_t h = 0; h < o->nhits; h++) dst[h].ss_off += ab;
+                memcpy(na.as<char>() + ab, o->arena.p, o->abytes);
+                for (size_t k = 0; k < o->recs.size(); k++) { S.hit_begin[o->recs[k]] = hb + o->begin[k]; S.hit_count[o->recs[k]] = o->count[k]; }
+                hb += o->nhits; ab += o->abytes;
+                o->hits.release(); o->arena.release();
+            }
+            S.hits.release(); S.arena.release();
+            S.hits = nh; S.arena = na;
+            S.hits_used = th; S.arena_used = ta;
+        }
+        if (nt_total && !getenv("MIRFOLD_RESULT_CAP_SCALE")) {
+            ctx->hits_per_nt = std::max(ctx->hits_per_nt, (double)S.hits_used / (double)nt_total);
+            ctx->arena_per_nt = std::max(ctx->arena_per_nt, (double)S.arena_used / (double)nt_total);
+        }
+        R->hits = S.hits; S.hits = HBuf();
+        R->arena = S.arena; S.arena = HBuf();
+        R->pub.hits = R->hits.as<mirfold_hit>();
+        R->pub.ss_arena = R->arena.as<char>();
+        if (R->arena.cap > abytes) R->arena.as<char>()[abytes] = 0;
+    } else {
+        R->pub.hits = nullptr;
+        R->pub.ss_arena = nullptr;
+    }
+    ht.mark("publish");
+    st.ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    R->pub.nseq = nseq;
+    R->pub.nhits = nhits;
+    R->pub.ss_bytes = abytes;
+    R->pub.hit_begin = R->hit_begin.data();
+    R->pub.hit_count = R->hit_count.data();
+    R->pub.total_mfe_dcal = R->totals.data();
+    R->pub.stats = st;
+    if (stats_out) *stats_out = st;
+    {
+        std::lock_guard<std::mutex> lk(ctx->pool_mu);
+        ctx->live_results++;
+    }
+    *out = &R.release()->pub;
+    return MIRFOLD_OK;
 }
 
 }  // namespace
@@ -705,6 +1031,7 @@ const char *mirfold_strerror(int code)
     case MIRFOLD_ERR_PARAMSET: return "unknown energy parameter set";
     case MIRFOLD_ERR_BACKTRACK: return "backtrack failed";
     case MIRFOLD_ERR_NOMEM: return "out of memory";
+    case MIRFOLD_ERR_CALLBACK: return "chunk callback returned non-zero";
     default: return "unknown error";
     }
 }
@@ -733,25 +1060,37 @@ int mirfold_open(mirfold_ctx **pctx, const int *device_ids, int n_devices, const
     DevParams *hp = new DevParams();
     build_params(*hp);
     int rc = MIRFOLD_OK;
-    for (int id : ids) {
-        Device D;
-        D.id = id;
-        cudaError_t e = cudaSetDevice(id);
-        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&D.stream, cudaStreamNonBlocking);
-        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&D.side, cudaStreamNonBlocking);
+    ctx->devs.resize(ids.size());
+    size_t made = 0;
+    for (size_t k = 0; k < ids.size() && rc == MIRFOLD_OK; k++) {
+        Device &D = ctx->devs[k];
+        D.id = ids[k];
+        made = k + 1;
+        // the same ordinal may be listed more than once (each entry is an independent pipeline sharing the GPU):
+        // the memory budget is split between the entries
+        int share = 0;
+        for (int id : ids) share += id == D.id;
+        int prio_lo = 0, prio_hi = 0;
+        cudaError_t e = cudaSetDevice(D.id);
+        if (e == cudaSuccess) e = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        for (int l = 0; l < 2; l++) if (e == cudaSuccess) e = D.lane[l].create(prio_hi);
+        if (e == cudaSuccess) e = cudaEventCreate(&D.ev_first);
+        if (e == cudaSuccess) e = cudaEventCreate(&D.ev_last);
         if (e == cudaSuccess) e = cudaMalloc(&D.dP, sizeof(DevParams));
         if (e == cudaSuccess) e = cudaMemcpy(D.dP, hp, sizeof(DevParams), cudaMemcpyHostToDevice);
         if (e == cudaSuccess) e = fill_configure_device();
-        for (auto &ev : D.ev) if (e == cudaSuccess) e = cudaEventCreate(&ev);
         size_t fr = 0, tot = 0;
         if (e == cudaSuccess) e = cudaMemGetInfo(&fr, &tot);
-        if (e != cudaSuccess) { ctx->last_error = cudaGetErrorString(e); rc = MIRFOLD_ERR_CUDA; D.release(); break; }
+        if (e != cudaSuccess) { ctx->last_error = cudaGetErrorString(e); cudaGetLastError(); rc = MIRFOLD_ERR_CUDA; break; }
         const char *env = getenv("MIRFOLD_MEM_BUDGET_MB");
-        D.mem_budget = env ? (size_t)atoll(env) << 20 : std::min<size_t>((size_t)(fr * 0.55), (size_t)64 << 30);
-        ctx->devs.push_back(D);
+        D.mem_budget = env ? (size_t)atoll(env) << 20 : std::min<size_t>((size_t)(fr * 0.60), (size_t)96 << 30) / (size_t)share;
     }
     delete hp;
-    if (rc != MIRFOLD_OK) { for (auto &D : ctx->devs) D.release(); delete ctx; return rc; }
+    if (rc != MIRFOLD_OK) {
+        for (size_t k = 0; k < made; k++) { cudaSetDevice(ctx->devs[k].id); ctx->devs[k].release(); }
+        delete ctx;
+        return rc;
+    }
     *pctx = ctx;
     return MIRFOLD_OK;
 }
@@ -759,305 +1098,180 @@ int mirfold_open(mirfold_ctx **pctx, const int *device_ids, int n_devices, const
 void mirfold_close(mirfold_ctx *ctx)
 {
     if (!ctx) return;
-    for (auto &D : ctx->devs) { cudaSetDevice(D.id); D.release(); }
-    for (auto &b : ctx->arena_pool) b.release();
-    for (auto &b : ctx->hits_pool) b.release();
-    delete ctx;
-}
-
-static void add_stats(mirfold_stats &a, const mirfold_stats &b)
-{
-    a.ms_h2d = std::max(a.ms_h2d, b.ms_h2d); a.ms_fill = std::max(a.ms_fill, b.ms_fill);
-    a.ms_f3 = std::max(a.ms_f3, b.ms_f3); a.ms_trace = std::max(a.ms_trace, b.ms_trace);
-    a.ms_d2h = std::max(a.ms_d2h, b.ms_d2h); a.ms_device = std::max(a.ms_device, b.ms_device);
-    a.nt += b.nt; a.cells += b.cells; a.tracebacks += b.tracebacks; a.kernel_launches += b.kernel_launches;
-    a.h2d_bytes += b.h2d_bytes; a.d2h_bytes += b.d2h_bytes; a.n_chunks += b.n_chunks; a.fill_units += b.fill_units;
-}
-
-static int fold_impl(mirfold_ctx *ctx, const char *seqs, const uint64_t *seq_off, uint32_t nseq, int span_L,
-                     const char *d_raw, bool download, void *stream, uint32_t flags, mirfold_result **out)
-{
-    static const bool env_wide = getenv("MIRFOLD_FORCE_WIDE") != nullptr;   // A/B runs of bench.py
-    const bool force_wide = (flags & MIRFOLD_FLAG_WIDE) != 0 || env_wide || span_L > MF16_MAX_SPAN;
-    if (!ctx || !out || !seq_off || (!seqs && !d_raw && nseq)) return MIRFOLD_ERR_ARG;
-    if (span_L < 5 || span_L > MF_MAX_SPAN) { ctx->last_error = "span_L out of range [5, 4096]"; return MIRFOLD_ERR_ARG; }
-    *out = nullptr;
-    const auto t0 = std::chrono::steady_clock::now();
-    const int G = d_raw ? 1 : (int)ctx->devs.size();
-    // ---- shard records over devices: greedy LPT on DP cells; no collectives
-    std::vector<std::vector<uint32_t>> shard(G);
-    if (G == 1) {
-        shard[0].resize(nseq);
-        for (uint32_t r = 0; r < nseq; r++) shard[0][r] = r;
-    } else {
-        std::vector<std::pair<uint64_t, uint32_t>> w(nseq);
-        for (uint32_t r = 0; r < nseq; r++) w[r] = {cells_of((int)(seq_off[r + 1] - seq_off[r]), span_L), r};
-        std::stable_sort(w.begin(), w.end(), [](const auto &a, const auto &b) { return a.first > b.first; });
-        std::vector<uint64_t> load(G, 0);
-        for (auto &x : w) {
-            int g = (int)(std::min_element(load.begin(), load.end()) - load.begin());
-            shard[g].push_back(x.second);
-            load[g] += x.first + 1;
-        }
-        for (auto &s : shard) std::sort(s.begin(), s.end());
-    }
-    std::vector<Partial> parts(G);
+    bool del;
     {
         std::lock_guard<std::mutex> lk(ctx->pool_mu);
-        for (int g = 0; g < G && !ctx->arena_pool.empty(); g++) { parts[g].arena = ctx->arena_pool.back(); ctx->arena_pool.pop_back(); }
-        for (int g = 0; g < G && !ctx->hits_pool.empty(); g++) { parts[g].hits = ctx->hits_pool.back(); ctx->hits_pool.pop_back(); }
+        if (ctx->closed) return;
+        ctx->closed = true;
+        for (auto &D : ctx->devs) { cudaSetDevice(D.id); cudaDeviceSynchronize(); D.release(); }
+        ctx->devs.clear();
+        for (auto &b : ctx->arena_pool) b.release();
+        for (auto &b : ctx->hits_pool) b.release();
+        ctx->arena_pool.clear(); ctx->hits_pool.clear();
+        del = ctx->live_results == 0;
     }
-    if (G == 1) run_device(ctx->devs[0], seqs, seq_off, shard[0], span_L, d_raw, download, (cudaStream_t)stream, force_wide, parts[0]);
-    else {
-        std::vector<std::thread> th;
-        for (int g = 0; g < G; g++)
-            th.emplace_back([&, g] { run_device(ctx->devs[g], seqs, seq_off, shard[g], span_L, nullptr, download, nullptr, force_wide, parts[g]); });
-        for (auto &t : th) t.join();
-    }
-    for (int g = 0; g < G; g++)
-        if (parts[g].err != MIRFOLD_OK) {
-            ctx->last_error = parts[g].errmsg;
-            for (auto &p : parts) { p.arena.release(); p.hits.release(); }
-            return parts[g].err;
-        }
-    HostTimer ht;
-    // ---- gather in input order
-    ResultOwner *R = new ResultOwner();
-    R->ctx = ctx;
-    R->hit_begin.assign((size_t)nseq + 1, 0);
-    R->hit_count.assign((size_t)nseq + 1, 0);
-    R->totals.assign(nseq, 0);
-    mirfold_stats st{};
-    uint64_t nhits = 0;
-    if (download) {
-        // Hits stay in the order the devices produced them (locus order inside a device, devices
-        // concatenated); a record finds its run through hit_begin / hit_count.
-        std::vector<uint64_t> arena_base(G, 0), hit_base(G, 0);
-        uint64_t abytes = 0;
-        for (int g = 0; g < G; g++) { arena_base[g] = abytes; abytes += parts[g].arena_bytes; hit_base[g] = nhits; nhits += parts[g].nhits; }
-        for (int g = 0; g < G; g++)
-            for (size_t k = 0; k < parts[g].recs.size(); k++) {
-                const uint32_t r = parts[g].recs[k];
-                R->hit_begin[r] = hit_base[g] + parts[g].rec_hit_begin[k];
-                R->hit_count[r] = parts[g].rec_hit_count[k];
-                R->totals[r] = parts[g].rec_total[k];
-            }
-        if (G == 1) {
-            R->hits = parts[0].hits;    // pinned table moves into the result
-            parts[0].hits = HBuf();
-            R->pub.hits = R->hits.as<mirfold_hit>();
-        } else {
-            // multi-device: one table and one arena for the caller; every device's part is copied (and its
-            // ss_off rebased) by its own thread into uninitialised buffers -- no zero fill, no serial pass
-            R->hits_m = (mirfold_hit *)malloc(sizeof(mirfold_hit) * (size_t)(nhits ? nhits : 1));
-            R->arena_m = (char *)malloc((size_t)abytes + 1);
-            if (!R->hits_m || !R->arena_m) {
-                free(R->hits_m); free(R->arena_m);
-                for (auto &p : parts) { p.arena.release(); p.hits.release(); }
-                delete R;
-                return MIRFOLD_ERR_NOMEM;
-            }
-            std::vector<std::thread> th;
-            for (int g = 0; g < G; g++)
-                th.emplace_back([&, g] {
-                    const mirfold_hit *src = parts[g].hits.as<mirfold_hit>();
-                    mirfold_hit *dst = R->hits_m + hit_base[g];
-                    const uint64_t ab = arena_base[g];
-                    for (uint64_t h = 0; h < parts[g].nhits; h++) { dst[h] = src[h]; dst[h].ss_off += ab; }
-                    if (parts[g].arena_bytes) memcpy(R->arena_m + ab, parts[g].arena.p, parts[g].arena_bytes);
-                });
-            for (auto &t : th) t.join();
-            R->arena_m[abytes] = 0;
-            for (int g = 0; g < G; g++) {
-                std::lock_guard<std::mutex> lk(ctx->pool_mu);
-                ctx->hits_pool.push_back(parts[g].hits);
-                parts[g].hits = HBuf();
-                ctx->arena_pool.push_back(parts[g].arena);
-                parts[g].arena = HBuf();
-            }
-            R->pub.hits = R->hits_m;
-            R->pub.ss_arena = R->arena_m;
-        }
-        if (G == 1) {
-            R->arena = parts[0].arena;  // pinned buffer moves into the result
-            parts[0].arena = HBuf();
-            R->pub.ss_arena = R->arena.as<char>();
-        }
-        R->pub.ss_bytes = abytes;
-    } else {
-        for (int g = 0; g < G; g++) { for (uint64_t v : parts[g].rec_hit_begin) nhits += v; R->pub.ss_bytes += parts[g].arena_bytes; }
-        for (auto &p : parts) {
-            std::lock_guard<std::mutex> lk(ctx->pool_mu);
-            if (p.arena.p) { ctx->arena_pool.push_back(p.arena); p.arena = HBuf(); }
-            if (p.hits.p) { ctx->hits_pool.push_back(p.hits); p.hits = HBuf(); }
-        }
-        R->pub.ss_arena = nullptr;
-        R->pub.hits = nullptr;
-    }
-    ht.mark("gather in input order");
-    for (int g = 0; g < G; g++) add_stats(st, parts[g].st);
-    st.n_devices = G;
-    st.ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    R->pub.nseq = nseq;
-    R->pub.nhits = nhits;
-    R->pub.hit_begin = R->hit_begin.data();
-    R->pub.hit_count = R->hit_count.data();
-    R->pub.total_mfe_dcal = R->totals.data();
-    R->pub.stats = st;
-    *out = &R->pub;
-    return MIRFOLD_OK;
+    if (del) delete ctx;   // otherwise the last mirfold_free_result() deletes it
 }
 
 int mirfold_fold(mirfold_ctx *ctx, const char *seqs, const uint64_t *seq_off, uint32_t nseq, int span_L, uint32_t flags,
                  mirfold_result **out)
 {
-    return fold_impl(ctx, seqs, seq_off, nseq, span_L, nullptr, true, nullptr, flags, out);
+    if (!out) return MIRFOLD_ERR_ARG;
+    FoldArgs A;
+    A.seqs = seqs; A.seq_off = seq_off; A.nseq = nseq; A.span_L = span_L; A.flags = flags; A.sink = SINK_SHARED;
+    return fold_engine(ctx, A, out, nullptr);
+}
+
+int mirfold_fold_stream(mirfold_ctx *ctx, const char *seqs, const uint64_t *seq_off, uint32_t nseq, int span_L, uint32_t flags,
+                        mirfold_chunk_fn fn, void *user, mirfold_stats *stats)
+{
+    if (!fn) return MIRFOLD_ERR_ARG;
+    FoldArgs A;
+    A.seqs = seqs; A.seq_off = seq_off; A.nseq = nseq; A.span_L = span_L; A.flags = flags; A.sink = SINK_STREAM;
+    A.fn = fn; A.user = user;
+    return fold_engine(ctx, A, nullptr, stats);
 }
 
 int mirfold_fold_device(mirfold_ctx *ctx, const void *d_seqs, const void *d_seq_off, const uint64_t *h_seq_off,
                         uint32_t nseq, int span_L, uint32_t flags, void *stream, mirfold_result **out)
 {
     (void)d_seq_off;
-    if (!d_seqs) return MIRFOLD_ERR_ARG;
-    return fold_impl(ctx, nullptr, h_seq_off, nseq, span_L, (const char *)d_seqs, false, stream, flags, out);
+    if (!d_seqs || !out || !ctx || ctx->closed) return MIRFOLD_ERR_ARG;
+    cudaSetDevice(ctx->devs[0].id);
+    if (cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) { cudaGetLastError(); return MIRFOLD_ERR_CUDA; }   // the caller's producer
+    std::vector<void *> d_raw(1, const_cast<void *>(d_seqs));
+    FoldArgs A;
+    A.seq_off = h_seq_off; A.nseq = nseq; A.span_L = span_L; A.flags = flags; A.sink = SINK_NONE;
+    A.d_raw = &d_raw; A.raw_off = h_seq_off; A.n_devices = 1;
+    return fold_engine(ctx, A, out, nullptr);
+}
+
+int mirfold_batch_upload(mirfold_ctx *ctx, const char *seqs, const uint64_t *seq_off, uint32_t nseq, int span_L, mirfold_batch **out)
+{
+    if (!ctx || !out || !seq_off || (!seqs && nseq) || ctx->closed) return MIRFOLD_ERR_ARG;
+    *out = nullptr;
+    if (span_L < 5 || span_L > MF_MAX_SPAN) { ctx->last_error = "span_L out of range [5, 4096]"; return MIRFOLD_ERR_ARG; }
+    int rc = validate_offsets(ctx, seq_off, nseq);
+    if (rc != MIRFOLD_OK) return rc;
+    std::unique_ptr<mirfold_batch> B(new mirfold_batch());
+    B->ctx = ctx; B->nseq = nseq; B->span_L = span_L;
+    B->h_off.assign(seq_off, seq_off + (size_t)nseq + 1);
+    const int G = (int)ctx->devs.size();
+    std::vector<uint64_t> load;
+    plan_shards(seq_off, nseq, span_L, G, B->shard, load);
+    B->raw_off.assign((size_t)nseq + 1, 0);
+    B->d_raw.assign((size_t)G, nullptr);
+    for (int g = 0; g < G; g++) {
+        uint64_t bytes = 0;
+        for (uint32_t r : B->shard[g]) { B->raw_off[r] = bytes; bytes += seq_off[r + 1] - seq_off[r]; }
+        std::vector<char> stage((size_t)bytes + 1);
+        for (uint32_t r : B->shard[g]) memcpy(stage.data() + B->raw_off[r], seqs + seq_off[r], (size_t)(seq_off[r + 1] - seq_off[r]));
+        cudaError_t e = cudaSetDevice(ctx->devs[g].id);
+        if (e == cudaSuccess) e = cudaMalloc(&B->d_raw[g], (size_t)bytes + 16);
+        if (e == cudaSuccess) e = cudaMemcpy(B->d_raw[g], stage.data(), (size_t)bytes, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            ctx->last_error = cudaGetErrorString(e);
+            cudaGetLastError();
+            mirfold_batch_free(B.release());
+            return e == cudaErrorMemoryAllocation ? MIRFOLD_ERR_NOMEM : MIRFOLD_ERR_CUDA;
+        }
+    }
+    *out = B.release();
+    return MIRFOLD_OK;
+}
+
+int mirfold_batch_fold(mirfold_ctx *ctx, mirfold_batch *B, uint32_t flags, int download, mirfold_result **out)
+{
+    if (!ctx || !B || B->ctx != ctx || !out) return MIRFOLD_ERR_ARG;
+    FoldArgs A;
+    A.seq_off = B->h_off.data(); A.nseq = B->nseq; A.span_L = B->span_L; A.flags = flags;
+    A.sink = download ? SINK_SHARED : SINK_NONE;
+    A.d_raw = &B->d_raw; A.raw_off = B->raw_off.data(); A.shard = &B->shard;
+    return fold_engine(ctx, A, out, nullptr);
+}
+
+void mirfold_batch_free(mirfold_batch *B)
+{
+    if (!B) return;
+    if (B->ctx && !B->ctx->closed)
+        for (size_t g = 0; g < B->d_raw.size() && g < B->ctx->devs.size(); g++)
+            if (B->d_raw[g]) { cudaSetDevice(B->ctx->devs[g].id); cudaFree(B->d_raw[g]); }
+    delete B;
+}
+
+int mirfold_plan_shards(const uint64_t *seq_off, uint32_t nseq, int span_L, int n_shards, uint32_t *shard_of, uint64_t *shard_cells)
+{
+    if (!seq_off || n_shards < 1 || span_L < 5) return MIRFOLD_ERR_ARG;
+    for (uint32_t r = 0; r < nseq; r++) if (seq_off[r + 1] < seq_off[r]) return MIRFOLD_ERR_ARG;
+    std::vector<std::vector<uint32_t>> shard;
+    std::vector<uint64_t> load;
+    plan_shards(seq_off, nseq, span_L, n_shards, shard, load);
+    for (int g = 0; g < n_shards; g++) {
+        if (shard_of) for (uint32_t r : shard[g]) shard_of[r] = (uint32_t)g;
+        if (shard_cells) shard_cells[g] = load[g] - shard[g].size();   // the plan weighs every record cells + 1
+    }
+    return MIRFOLD_OK;
 }
 
 void mirfold_free_result(mirfold_result *res)
 {
     if (!res) return;
     ResultOwner *R = reinterpret_cast<ResultOwner *>(res);
-    if (R->arena.p && R->ctx) {
-        std::lock_guard<std::mutex> lk(R->ctx->pool_mu);
-        if (R->ctx->arena_pool.size() < 4) { R->ctx->arena_pool.push_back(R->arena); R->arena = HBuf(); }
-    }
-    if (R->hits.p && R->ctx) {
-        std::lock_guard<std::mutex> lk(R->ctx->pool_mu);
-        if (R->ctx->hits_pool.size() < 4) { R->ctx->hits_pool.push_back(R->hits); R->hits = HBuf(); }
+    mirfold_ctx *ctx = R->ctx;
+    bool del = false;
+    {
+        std::lock_guard<std::mutex> lk(ctx->pool_mu);
+        pool_give(ctx, ctx->arena_pool, R->arena);
+        pool_give(ctx, ctx->hits_pool, R->hits);
+        ctx->live_results--;
+        del = ctx->closed && ctx->live_results == 0;
     }
     R->arena.release();
     R->hits.release();
-    free(R->hits_m);
-    free(R->arena_m);
     delete R;
-}
-
-int mirfold_format_records(const mirfold_result *res, const char *seqs, const uint64_t *seq_off, uint32_t nseq, char **text,
-                           uint64_t **rec_off)
-{
-    if (!res || !text || !rec_off || !seq_off || (!seqs && nseq) || res->nseq != nseq) return MIRFOLD_ERR_ARG;
-    if (res->nhits && !res->ss_arena) return MIRFOLD_ERR_ARG;   // device-resident results carry no structures
-    *text = nullptr; *rec_off = nullptr;
-    uint64_t *off = (uint64_t *)malloc(sizeof(uint64_t) * ((size_t)nseq + 1));
-    if (!off) return MIRFOLD_ERR_NOMEM;
-    // every "(%6.2f)" field is 8 characters for |E| < 1000 kcal/mol and grows with the integer part beyond;
-    // sizes are computed exactly with the same snprintf calls that fill the buffer
-    auto hit_line = [&](char *dst, size_t cap, const mirfold_hit &h) {
-        // dot-bracket, then " (%6.2f) %4d\n"
-        if (dst) memcpy(dst, res->ss_arena + h.ss_off, (size_t)h.len);
-        char tail[64];
-        const int k = snprintf(tail, sizeof tail, " (%6.2f) %4d\n", h.mfe_dcal / 100., h.start);
-        if (dst) memcpy(dst + h.len, tail, (size_t)k);
-        (void)cap;
-        return (size_t)h.len + (size_t)k;
-    };
-    auto total_line = [&](char *dst, uint32_t r) {
-        const size_t n = (size_t)(seq_off[r + 1] - seq_off[r]);
-        if (dst) {
-            const char *src = seqs + seq_off[r];
-            for (size_t k = 0; k < n; k++) {
-                char ch = src[k];
-                if (ch >= 'a' && ch <= 'z') ch = (char)(ch - 32);
-                dst[k] = ch == 'T' ? 'U' : ch;
-            }
-            dst[n] = '\n';
-        }
-        char tail[64];
-        const int k = snprintf(tail, sizeof tail, " (%6.2f)\n", res->total_mfe_dcal[r] / 100.);
-        if (dst) memcpy(dst + n + 1, tail, (size_t)k);
-        return n + 1 + (size_t)k;
-    };
-    const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
-    const unsigned nthr = nseq < 256 ? 1u : hw;
-    auto for_ranges = [&](auto &&fn) {
-        std::vector<std::thread> th;
-        for (unsigned t = 0; t < nthr; t++) {
-            const uint32_t lo = (uint32_t)((uint64_t)nseq * t / nthr), hi = (uint32_t)((uint64_t)nseq * (t + 1) / nthr);
-            if (nthr == 1) fn(lo, hi);
-            else th.emplace_back(fn, lo, hi);
-        }
-        for (auto &x : th) x.join();
-    };
-    // pass 1: sizes
-    for_ranges([&](uint32_t lo, uint32_t hi) {
-        for (uint32_t r = lo; r < hi; r++) {
-            size_t b = 0;
-            for (uint64_t h = res->hit_begin[r]; h < res->hit_begin[r] + res->hit_count[r]; h++) b += hit_line(nullptr, 0, res->hits[h]);
-            off[r + 1] = b + total_line(nullptr, r);
-        }
-    });
-    off[0] = 0;
-    for (uint32_t r = 0; r < nseq; r++) off[r + 1] += off[r];
-    char *buf = (char *)malloc((size_t)off[nseq] + 1);
-    if (!buf) { free(off); return MIRFOLD_ERR_NOMEM; }
-    // pass 2: fill
-    for_ranges([&](uint32_t lo, uint32_t hi) {
-        for (uint32_t r = lo; r < hi; r++) {
-            char *dst = buf + off[r];
-            for (uint64_t h = res->hit_begin[r]; h < res->hit_begin[r] + res->hit_count[r]; h++) dst += hit_line(dst, 0, res->hits[h]);
-            total_line(dst, r);
-        }
-    });
-    buf[off[nseq]] = 0;
-    *text = buf; *rec_off = off;
-    return MIRFOLD_OK;
-}
-
-void mirfold_free_text(char *text, uint64_t *rec_off)
-{
-    free(text);
-    free(rec_off);
+    if (del) delete ctx;
 }
 
 int mirfold_debug_matrices(mirfold_ctx *ctx, const char *seq, uint32_t n, int span_L, uint32_t flags, int32_t *c, int32_t *m,
                            int32_t *f3)
 {
-    if (!ctx || !seq || n < 5 || !c || !m || !f3) return MIRFOLD_ERR_ARG;
+    if (!ctx || ctx->closed || !seq || n < 5 || !c || !m || !f3) return MIRFOLD_ERR_ARG;
     Device &D = ctx->devs[0];
-#undef CK
+    Lane &Ln = D.lane[0];
 #define CK(call)                                                                  \
     do {                                                                          \
         cudaError_t e_ = (call);                                                  \
-        if (e_ != cudaSuccess) { ctx->last_error = cudaGetErrorString(e_); return MIRFOLD_ERR_CUDA; } \
+        if (e_ != cudaSuccess) { ctx->last_error = cudaGetErrorString(e_); cudaGetLastError(); return MIRFOLD_ERR_CUDA; } \
     } while (0)
     CK(cudaSetDevice(D.id));
-    cudaStream_t st = D.stream;
+    cudaStream_t st = Ln.s_lo;
     LocusDesc d{};
     const unsigned long long cells = shape_locus(d, (int)n, span_L);
     std::vector<LocusDesc> units;
     int bucket_first[5], max_n = 0;
     const unsigned long long ring_elems = build_fill_units(&d, 1, units, bucket_first, max_n);
     const int nu = (int)units.size();
-    CK(D.raw.ensure(n)); CK(D.loci.ensure(sizeof d)); CK(D.codes.ensure(n + 3)); CK(D.F.ensure((n + 3) * 4));
-    CK(D.C.ensure(cells * 4)); CK(D.M.ensure(cells * 4)); CK(D.Mp.ensure(cells * 4));
-    CK(D.ring.ensure((size_t)ring_elems * 4));
-    CK(D.units.ensure(sizeof(LocusDesc) * (size_t)nu + 64));
-    CK(cudaMemcpyAsync(D.raw.p, seq, n, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(D.loci.p, &d, sizeof d, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(D.units.p, units.data(), sizeof(LocusDesc) * (size_t)nu, cudaMemcpyHostToDevice, st));
-    const LocusDesc *dl = D.loci.as<LocusDesc>();
-    CK(launch_prepare(D.raw.as<char>(), dl, 1, n + 3, D.codes.as<unsigned char>(), D.F.as<int>(), st));
-    CK(D.fillflags.ensure((size_t)nu * 4 + 4));
-    CK(cudaMemsetAsync(D.fillflags.p, 0, (size_t)nu * 4 + 4, st));
-    FillLaunch fa{D.units.as<LocusDesc>(), nu, max_n, D.codes.as<unsigned char>(), D.C.as<int>(), D.M.as<int>(), D.ring.as<int>(),
-                  D.Mp.as<unsigned int>(), D.dP, {0, 0, 0, 0, 0}, D.fillflags.as<int>(),
+    CK(Ln.raw.ensure(n)); CK(Ln.loci.ensure(sizeof d)); CK(Ln.codes.ensure(n + 3)); CK(Ln.F.ensure((n + 3) * 4));
+    CK(Ln.C.ensure(cells * 4)); CK(Ln.M.ensure(cells * 4)); CK(Ln.Mp.ensure(cells * 4));
+    CK(Ln.ring.ensure((size_t)ring_elems * 4));
+    CK(Ln.units.ensure(sizeof(LocusDesc) * (size_t)nu + 64));
+    CK(cudaMemcpyAsync(Ln.raw.p, seq, n, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(Ln.loci.p, &d, sizeof d, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(Ln.units.p, units.data(), sizeof(LocusDesc) * (size_t)nu, cudaMemcpyHostToDevice, st));
+    const LocusDesc *dl = Ln.loci.as<LocusDesc>();
+    CK(launch_prepare(Ln.raw.as<char>(), dl, 1, n + 3, Ln.codes.as<unsigned char>(), Ln.F.as<int>(), st));
+    CK(Ln.fillflags.ensure((size_t)nu * 4 + 4));
+    CK(cudaMemsetAsync(Ln.fillflags.p, 0, (size_t)nu * 4 + 4, st));
+    FillLaunch fa{Ln.units.as<LocusDesc>(), nu, max_n, Ln.codes.as<unsigned char>(), Ln.C.as<int>(), Ln.M.as<int>(), Ln.ring.as<int>(),
+                  Ln.Mp.as<unsigned int>(), D.dP, {0, 0, 0, 0, 0}, Ln.fillflags.as<int>(),
                   ((flags & MIRFOLD_FLAG_WIDE) || span_L > MF16_MAX_SPAN) ? 1 : 0, env_opts()};
     for (int b = 0; b < 5; b++) fa.bucket_first[b] = bucket_first[b];
     CK(launch_fill(fa, st));
-    CK(launch_f3(dl, 1, d.n > MF_TILE_LEN ? 1 : 0, d.Ls, D.codes.as<unsigned char>(), D.C.as<int>(), D.F.as<int>(), D.dP, st));
+    CK(launch_f3(dl, 1, d.n > MF_TILE_LEN ? 1 : 0, d.Ls, Ln.codes.as<unsigned char>(), Ln.C.as<int>(), Ln.F.as<int>(), D.dP, st));
     std::vector<int> hc(cells), hm(cells), hf(n + 3);
-    CK(cudaMemcpyAsync(hc.data(), D.C.p, cells * 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(hm.data(), D.M.p, cells * 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(hf.data(), D.F.p, (n + 3) * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(hc.data(), Ln.C.p, cells * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(hm.data(), Ln.M.p, cells * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(hf.data(), Ln.F.p, (n + 3) * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     const int W = d.Ls + 6;
     for (size_t k = 0; k < (size_t)(n + 2) * W; k++) c[k] = m[k] = MF_INF;
@@ -1080,12 +1294,24 @@ int mirfold_debug_matrices(mirfold_ctx *ctx, const char *seq, uint32_t n, int sp
 
 int mirfold_int_peak(mirfold_ctx *ctx, double *addmin_terms_per_s, double *dpx_terms_per_s)
 {
-    if (!ctx || !addmin_terms_per_s || !dpx_terms_per_s) return MIRFOLD_ERR_ARG;
+    if (!ctx || ctx->closed || !addmin_terms_per_s || !dpx_terms_per_s) return MIRFOLD_ERR_ARG;
     Device &D = ctx->devs[0];
     cudaSetDevice(D.id);
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, D.id);
-    cudaError_t e = run_int_peak(D.stream, sms, addmin_terms_per_s, dpx_terms_per_s);
+    cudaError_t e = run_int_peak(D.lane[0].s_lo, sms, addmin_terms_per_s, dpx_terms_per_s, nullptr);
+    if (e != cudaSuccess) { ctx->last_error = cudaGetErrorString(e); return MIRFOLD_ERR_CUDA; }
+    return MIRFOLD_OK;
+}
+
+int mirfold_int_peak2(mirfold_ctx *ctx, double *addmin_terms_per_s, double *dpx_terms_per_s, double *s16x2_terms_per_s)
+{
+    if (!ctx || ctx->closed || !addmin_terms_per_s || !dpx_terms_per_s || !s16x2_terms_per_s) return MIRFOLD_ERR_ARG;
+    Device &D = ctx->devs[0];
+    cudaSetDevice(D.id);
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, D.id);
+    cudaError_t e = run_int_peak(D.lane[0].s_lo, sms, addmin_terms_per_s, dpx_terms_per_s, s16x2_terms_per_s);
     if (e != cudaSuccess) { ctx->last_error = cudaGetErrorString(e); return MIRFOLD_ERR_CUDA; }
     return MIRFOLD_OK;
 }
@@ -1093,7 +1319,7 @@ int mirfold_int_peak(mirfold_ctx *ctx, double *addmin_terms_per_s, double *dpx_t
 int mirfold_duplex(mirfold_ctx *ctx, const char *ss_arena, uint64_t ss_bytes, const mirfold_duplex_query *queries,
                    uint64_t nq, mirfold_duplex_verdict *verdicts)
 {
-    if (!ctx || (!ss_arena && ss_bytes) || (!queries && nq) || (!verdicts && nq)) return MIRFOLD_ERR_ARG;
+    if (!ctx || ctx->closed || (!ss_arena && ss_bytes) || (!queries && nq) || (!verdicts && nq)) return MIRFOLD_ERR_ARG;
     if (nq == 0) return MIRFOLD_OK;
     int maxlen = 1;
     for (uint64_t k = 0; k < nq; k++) {
@@ -1105,37 +1331,19 @@ int mirfold_duplex(mirfold_ctx *ctx, const char *ss_arena, uint64_t ss_bytes, co
     }
     if (maxlen > 32000) { ctx->last_error = "mirfold_duplex: structure longer than 32000"; return MIRFOLD_ERR_ARG; }
     Device &D = ctx->devs[0];
-    cudaStream_t st = D.stream;
+    cudaStream_t st = D.lane[0].s_hi;
     CK(cudaSetDevice(D.id));
-    CK(D.o_arena.ensure(ss_bytes + 16));
-    CK(D.scan_in.ensure(nq * sizeof(mirfold_duplex_query)));
-    CK(D.scan_out.ensure(nq * sizeof(mirfold_duplex_verdict)));
-    CK(cudaMemcpyAsync(D.o_arena.p, ss_arena, ss_bytes, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(D.scan_in.p, queries, nq * sizeof(mirfold_duplex_query), cudaMemcpyHostToDevice, st));
-    CK(launch_duplex(D.o_arena.as<char>(), D.scan_in.as<mirfold_duplex_query>(), nq, D.scan_out.as<mirfold_duplex_verdict>(),
+    CK(D.duplex_arena.ensure(ss_bytes + 16));
+    CK(D.duplex_q.ensure(nq * sizeof(mirfold_duplex_query)));
+    CK(D.duplex_v.ensure(nq * sizeof(mirfold_duplex_verdict)));
+    CK(cudaMemcpyAsync(D.duplex_arena.p, ss_arena, ss_bytes, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(D.duplex_q.p, queries, nq * sizeof(mirfold_duplex_query), cudaMemcpyHostToDevice, st));
+    CK(launch_duplex(D.duplex_arena.as<char>(), D.duplex_q.as<mirfold_duplex_query>(), nq, D.duplex_v.as<mirfold_duplex_verdict>(),
                      (maxlen + 7) & ~7, st));
-    CK(cudaMemcpyAsync(verdicts, D.scan_out.p, nq * sizeof(mirfold_duplex_verdict), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(verdicts, D.duplex_v.p, nq * sizeof(mirfold_duplex_verdict), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return MIRFOLD_OK;
 }
-
-const char *mirfold_duplex_fail_name(int code)
-{
-    static const char *names[] = {"PASS",
-                                  "FAIL_STRUCTURE_MATCHED_BASES",
-                                  "FAIL_STRUCTURE_MATURE_NOT_IN_FOLD_REGION",
-                                  "FAIL_STRUCTURE_MATURE_NOT_IN_ONE_ARM",
-                                  "FAIL_STRUCTURE_MATURE_MATCH_SMALL_THAN_14",
-                                  "FAIL_STRUCTURE_MATURE_STAR_OVERLAP",
-                                  "FAIL_STRUCTURE_STAR_OUT_OF_FOLD_REGION",
-                                  "FAIL_STRUCTURE_STAR_NOT_IN_ONE_ARM",
-                                  "FAIL_STRUCTURE_TOO_MANY_BULGE_OR_LOOP",
-                                  "FAIL_STRUCTURE_MAX_BULGE_LARGE_THAN_2",
-                                  "FAIL_STRUCTURE_TOTAL_LOOP_SIZE_LARGER_THAN_5",
-                                  "FAIL_STRUCTURE_NUM_BULGE_MORE_THAN_2"};
-    if (code >= 0 && code < 12) return names[code];
-    if (code == 100) return "EXCEPTION_UNBALANCED_STRUCTURE";
-    return "";
-}
+#undef CK
 
 }  // extern "C"

@@ -169,7 +169,7 @@ cudaError_t launch_emit(const TraceBuffers &b, cudaStream_t st);
 struct mirfold_hit;
 cudaError_t launch_pack(const TraceBuffers &b, const unsigned long long *ss_off, const unsigned long long *hit_idx,
                         char *arena, mirfold_hit *out_hits, unsigned long long arena_base, cudaStream_t st);
-cudaError_t run_int_peak(cudaStream_t st, int sm_count, double *addmin, double *dpx);
+cudaError_t run_int_peak(cudaStream_t st, int sm_count, double *addmin, double *dpx, double *s16x2);
 struct mirfold_duplex_query;
 struct mirfold_duplex_verdict;
 cudaError_t launch_duplex(const char *arena, const mirfold_duplex_query *qs, unsigned long long nq,

@@ -17,7 +17,8 @@ __global__ void __launch_bounds__(256) k_int_peak(int *out, int iters, int c)
                 asm volatile("add.s32 %0, %1, %2;" : "=r"(t) : "r"(acc[(k + 1) & 15]), "r"(c));
                 asm volatile("min.s32 %0, %1, %2;" : "=r"(acc[k]) : "r"(t), "r"(acc[k]));
             }
-            else acc[k] = __viaddmin_s32(acc[(k + 1) & 15], c, acc[k]);
+            else if (MODE == 1) acc[k] = __viaddmin_s32(acc[(k + 1) & 15], c, acc[k]);
+            else acc[k] = (int)__viaddmin_s16x2((unsigned)acc[(k + 1) & 15], (unsigned)c, (unsigned)acc[k]);   // VIADDMNMX.S16x2: two terms
         }
     }
     int r = 0;
@@ -26,8 +27,8 @@ __global__ void __launch_bounds__(256) k_int_peak(int *out, int iters, int c)
     if (r == 0x7fffffff) out[0] = r;  // never true in practice; keeps the loop alive
 }
 
-// returns terms/s for both variants (best of `reps`)
-cudaError_t run_int_peak(cudaStream_t st, int sm_count, double *addmin, double *dpx)
+// returns terms/s for the variants (best of `reps`); s16x2 (may be NULL) counts two terms per instruction
+cudaError_t run_int_peak(cudaStream_t st, int sm_count, double *addmin, double *dpx, double *s16x2)
 {
     int *d = nullptr;
     cudaError_t e = cudaMalloc(&d, 4);
@@ -35,23 +36,25 @@ cudaError_t run_int_peak(cudaStream_t st, int sm_count, double *addmin, double *
     cudaEvent_t a, b;
     cudaEventCreate(&a); cudaEventCreate(&b);
     const int blocks = sm_count * 8, iters = 4096;
-    double best[2] = {0, 0};
-    for (int mode = 0; mode < 2; mode++)
+    double best[3] = {0, 0, 0};
+    for (int mode = 0; mode < (s16x2 ? 3 : 2); mode++)
         for (int rep = 0; rep < 5; rep++) {
             cudaEventRecord(a, st);
             if (mode == 0) k_int_peak<0><<<blocks, 256, 0, st>>>(d, iters, 3 + rep);
-            else k_int_peak<1><<<blocks, 256, 0, st>>>(d, iters, 3 + rep);
+            else if (mode == 1) k_int_peak<1><<<blocks, 256, 0, st>>>(d, iters, 3 + rep);
+            else k_int_peak<2><<<blocks, 256, 0, st>>>(d, iters, 3 + rep);
             cudaEventRecord(b, st);
             e = cudaEventSynchronize(b);
             if (e != cudaSuccess) break;
             float ms = 0;
             cudaEventElapsedTime(&ms, a, b);
-            const double terms = (double)blocks * 256.0 * 16.0 * iters;
+            const double terms = (double)blocks * 256.0 * 16.0 * iters * (mode == 2 ? 2.0 : 1.0);
             if (rep > 0) best[mode] = fmax(best[mode], terms / (ms * 1e-3));
         }
     cudaEventDestroy(a); cudaEventDestroy(b);
     cudaFree(d);
     *addmin = best[0];
     *dpx = best[1];
+    if (s16x2) *s16x2 = best[2];
     return e;
 }

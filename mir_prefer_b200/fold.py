@@ -21,16 +21,19 @@ from ._lib import MirfoldError
 
 DEFAULT_PARAMSET = b"vienna-1.8.5-d1"
 FLAG_WIDE = 1   # MIRFOLD_FLAG_WIDE: force the 32-bit fill kernel (results are identical)
+FLAG_SERIAL = 2  # MIRFOLD_FLAG_SERIAL: one chunk at a time per device (disjoint per-stage device times)
+DUPLEX_EXCEPTION = "EXCEPTION_UNBALANCED_STRUCTURE"   # verdict where the reference's get_maturestar_info raises
 HIT_DTYPE = np.dtype([("start", "<i4"), ("len", "<i4"), ("mfe_dcal", "<i4"), ("reserved", "<i4"), ("ss_off", "<u8")])
 
 
 class FoldResult:
     """Owns a mirfold_result.  Hit order inside a record is RNALfold's print order."""
 
-    def __init__(self, lib, ptr, nseq, inputs=None):
+    def __init__(self, lib, ptr, nseq, inputs=None, owner=None):
         self._lib = lib
         self._ptr = ptr
         self._inputs = inputs          # (uint8 buffer, uint64 offsets) the result was folded from
+        self._owner = owner            # the MirFold it came from (the C library also lets a result outlive its context)
         r = ptr.contents
         self.nseq = int(r.nseq)
         self.nhits = int(r.nhits)
@@ -172,6 +175,75 @@ def format_record(seq_token, hits, total_dcal):
     return "".join(out)
 
 
+class FoldChunk:
+    """One chunk handed to a fold_stream() callback: numpy views that are only valid during the call."""
+
+    def __init__(self, c):
+        n, nh = int(c.n_records), int(c.nhits)
+        self.device = int(c.device)
+        self.records = np.ctypeslib.as_array(c.record, shape=(n,)) if n else np.zeros(0, np.uint32)
+        self.hit_begin = np.ctypeslib.as_array(c.hit_begin, shape=(n,)) if n else np.zeros(0, np.uint64)
+        self.hit_count = np.ctypeslib.as_array(c.hit_count, shape=(n,)) if n else np.zeros(0, np.uint32)
+        self.total_mfe_dcal = np.ctypeslib.as_array(c.total_mfe_dcal, shape=(n,)) if n else np.zeros(0, np.int32)
+        self.nhits, self.ss_bytes = nh, int(c.ss_bytes)
+        if nh:
+            raw = np.ctypeslib.as_array(C.cast(c.hits, C.POINTER(C.c_uint8)), shape=(nh * C.sizeof(_lib.Hit),))
+            self.hit_table = raw.view(HIT_DTYPE)
+            self.arena = np.ctypeslib.as_array(C.cast(c.ss_arena, C.POINTER(C.c_uint8)), shape=(self.ss_bytes,))
+        else:
+            self.hit_table, self.arena = np.zeros(0, HIT_DTYPE), np.zeros(0, np.uint8)
+
+    def hits(self, k):
+        """[(dot_bracket, energy_dcal, start_1based)] of the chunk's k-th record (input record self.records[k])."""
+        b = int(self.hit_begin[k])
+        out = []
+        for h in self.hit_table[b:b + int(self.hit_count[k])]:
+            o, n = int(h["ss_off"]), int(h["len"])
+            out.append((self.arena[o:o + n].tobytes().decode("ascii"), int(h["mfe_dcal"]), int(h["start"])))
+        return out
+
+
+class Batch:
+    """Records sharded over the context's devices with their sequences resident in HBM (mirfold_batch_*)."""
+
+    def __init__(self, owner, ptr, nseq, inputs):
+        self._owner, self._ptr, self.nseq, self._inputs = owner, ptr, nseq, inputs
+
+    def fold(self, download=False, flags=0):
+        res = C.POINTER(_lib.Result)()
+        rc = self._owner._lib.mirfold_batch_fold(self._owner._ctx, self._ptr, int(flags), 1 if download else 0, C.byref(res))
+        if rc != 0:
+            self._owner._raise(rc)
+        return FoldResult(self._owner._lib, res, self.nseq, inputs=self._inputs if download else None, owner=self._owner)
+
+    def close(self):
+        if self._ptr:
+            self._owner._lib.mirfold_batch_free(self._ptr)
+            self._ptr = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
+def plan_shards(lengths, span, n_shards):
+    """The library's own shard plan (mirfold_plan_shards: greedy LPT by DP cells -- what a context of n_shards devices
+    does with these records).  Host-only.  Returns (shard_of[nseq] uint32, shard_cells[n_shards] uint64)."""
+    lib = _lib.load()
+    lengths = np.asarray(lengths, np.uint64)
+    off = np.zeros(len(lengths) + 1, np.uint64)
+    off[1:] = np.cumsum(lengths, dtype=np.uint64)
+    shard_of = np.zeros(len(lengths), np.uint32)
+    cells = np.zeros(n_shards, np.uint64)
+    rc = lib.mirfold_plan_shards(off.ctypes.data_as(C.POINTER(C.c_uint64)), len(lengths), int(span), int(n_shards),
+                                 shard_of.ctypes.data_as(C.POINTER(C.c_uint32)), cells.ctypes.data_as(C.POINTER(C.c_uint64)))
+    if rc != 0:
+        raise MirfoldError(rc, lib.mirfold_strerror(rc).decode())
+    return shard_of, cells
+
+
 class MirFold:
     """A libmirfold context (one per process; `devices` = CUDA ordinals, default current device)."""
 
@@ -204,7 +276,7 @@ class MirFold:
     @staticmethod
     def pack(seqs):
         """list of str/bytes -> (uint8 buffer, uint64 offsets)."""
-        bs = [s.encode("ascii") if isinstance(s, str) else bytes(s) for s in seqs]
+        bs = [s.encode("latin-1", "replace") if isinstance(s, str) else bytes(s) for s in seqs]
         off = np.zeros(len(bs) + 1, np.uint64)
         if bs:
             off[1:] = np.cumsum([len(b) for b in bs], dtype=np.uint64)
@@ -221,7 +293,45 @@ class MirFold:
                                     nseq, int(span), int(flags), C.byref(res))
         if rc != 0:
             self._raise(rc)
-        return FoldResult(self._lib, res, nseq, inputs=(buf, off))
+        return FoldResult(self._lib, res, nseq, inputs=(buf, off), owner=self)
+
+    def fold_stream(self, buf, off, span, callback, flags=0):
+        """mirfold_fold_stream(): fold like fold_packed() but hand the results to callback(FoldChunk) chunk by chunk
+        while later chunks are still computing (the whole result never sits in host memory; replaces the
+        reference's 2*CHECKPOINT_SIZE-line loop, miR_PREFeR.py:3022-3044).  Chunks arrive in completion order;
+        FoldChunk.records names the input records.  Returns the call's stats dict."""
+        buf = np.ascontiguousarray(buf, np.uint8)
+        off = np.ascontiguousarray(off, np.uint64)
+        err = []
+
+        def tramp(_user, cptr):
+            try:
+                callback(FoldChunk(cptr.contents))
+                return 0
+            except BaseException as e:   # noqa: BLE001 -- must not propagate through the C frames
+                err.append(e)
+                return 1
+
+        fn = _lib.CHUNK_FN(tramp)
+        st = _lib.Stats()
+        rc = self._lib.mirfold_fold_stream(self._ctx, buf.ctypes.data_as(C.c_void_p), off.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                           len(off) - 1, int(span), int(flags), fn, None, C.byref(st))
+        if err:
+            raise err[0]
+        if rc != 0:
+            self._raise(rc)
+        return st.as_dict()
+
+    def upload(self, buf, off, span):
+        """mirfold_batch_upload(): shard the records over the context's devices and keep their sequences in HBM."""
+        buf = np.ascontiguousarray(buf, np.uint8)
+        off = np.ascontiguousarray(off, np.uint64)
+        ptr = C.c_void_p()
+        rc = self._lib.mirfold_batch_upload(self._ctx, buf.ctypes.data_as(C.c_void_p), off.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                            len(off) - 1, int(span), C.byref(ptr))
+        if rc != 0:
+            self._raise(rc)
+        return Batch(self, ptr, len(off) - 1, (buf, off))
 
     def fold(self, seqs, span, flags=0):
         buf, off = self.pack(seqs)
@@ -235,7 +345,15 @@ class MirFold:
                                            len(off) - 1, int(span), int(flags), C.c_void_p(stream or 0), C.byref(res))
         if rc != 0:
             self._raise(rc)
-        return FoldResult(self._lib, res, len(off) - 1)
+        return FoldResult(self._lib, res, len(off) - 1, owner=self)
+
+    def int_peak2(self):
+        """(add+min, DPX s32, VIADDMNMX.S16x2) min-plus terms/s on this context's device."""
+        a, b, c = C.c_double(), C.c_double(), C.c_double()
+        rc = self._lib.mirfold_int_peak2(self._ctx, C.byref(a), C.byref(b), C.byref(c))
+        if rc != 0:
+            self._raise(rc)
+        return a.value, b.value, c.value
 
     def int_peak(self):
         """Measured integer-issue roofline: (add+min terms/s, DPX terms/s) on this context's device."""
@@ -265,7 +383,8 @@ class MirFold:
         queries: iterable of (ss, (m0, m1), foldstart, regionstart, regionend, strand) -- the reference's
         argument order minus the redundant foldend.  Returns, per query, exactly what the reference
         returns: the 9-tuple (star_start, star_end, fold_start, fold_end, star_ss, prime5, mature_ss,
-        total_dots, total_bps) in genome coordinates, or the FAIL_* string."""
+        total_dots, total_bps) in genome coordinates, or the FAIL_* string; DUPLEX_EXCEPTION marks a pair on
+        which the reference's function raises (unbalanced brackets inside the mature or its partner region)."""
         queries = list(queries)
         nq = len(queries)
         if nq == 0:
@@ -306,9 +425,7 @@ class MirFold:
                 name = names.get(c)
                 if name is None:
                     name = names[c] = self._lib.mirfold_duplex_fail_name(c).decode()
-                if c == 100:
-                    raise MirfoldError(-3, "duplex query %d: %s (the reference raises here)" % (k, name))
-                res.append(name)
+                res.append(name)   # code 100 = DUPLEX_EXCEPTION: the reference raises for this pair (see DuplexTable)
             else:
                 ss = q[0]
                 res.append((cols["star_start"][k], cols["star_end"][k], cols["fold_start"][k], cols["fold_end"][k],
@@ -317,8 +434,10 @@ class MirFold:
         return res
 
     # ---- RNALfold CLI contract -------------------------------------------------------------
-    def fold_text_bytes(self, text, span):
-        """RNALfold-identical stdout (bytes) for RNALfold-style stdin text (`RNALfold -L span`)."""
+    def fold_text_bytes(self, text, span, encoding=None):
+        """RNALfold-identical stdout (bytes) for RNALfold-style stdin text (`RNALfold -L span`).  `encoding`:
+        how echoed header lines go back to bytes (default utf-8 with surrogateescape; "latin-1" for text that was
+        decoded from raw bytes as latin-1)."""
         items = parse_rnalfold_input(text)
         seqs = [tok for kind, tok in items if kind == "seq"]
         out = []
@@ -328,7 +447,7 @@ class MirFold:
             r = 0
             for kind, tok in items:
                 if kind == "echo":
-                    out.append(tok.encode("utf-8", "surrogateescape") + b"\n")
+                    out.append((tok.encode(encoding) if encoding else tok.encode("utf-8", "surrogateescape")) + b"\n")
                 else:
                     out.append(view[int(offs[r]):int(offs[r + 1])])
                     r += 1
@@ -338,12 +457,31 @@ class MirFold:
         """RNALfold-identical stdout for RNALfold-style stdin text (`RNALfold -L span`)."""
         return self.fold_text_bytes(text, span).decode("utf-8", "surrogateescape")
 
-    def fold_fasta_files(self, fastas, outnames, span):
-        """fold_use_RNALfold() replacement: fold every FASTA shard, write RNALfold-format outputs."""
+    def fold_fasta_files(self, fastas, outnames, span, batch_lines=200000):
+        """fold_use_RNALfold() replacement (miR_PREFeR.py:3047-3119): fold every FASTA shard and write the
+        RNALfold-format output files.  Like the reference's fold(), a shard is processed `batch_lines` input
+        lines at a time (its 2*CHECKPOINT_SIZE, :3085-3098) and appended to `<outname>.tmp`, which is renamed
+        when the shard is complete (:3098) -- a failing shard leaves no output file and no .tmp behind.
+        Shards are read as bytes: header lines are echoed byte for byte, '\r' is not a line end."""
         for fa, outname in zip(fastas, outnames):
-            with open(fa, encoding="utf-8", errors="surrogateescape") as f:   # header bytes pass through unchanged
-                text = f.read()
-            with open(outname + ".tmp", "wb") as f:
-                f.write(self.fold_text_bytes(text, span))
-            os.rename(outname + ".tmp", outname)   # atomic, like MP:3098
+            tmp = outname + ".tmp"
+            try:
+                with open(fa, "rb") as fin, open(tmp, "wb") as fout:
+                    while True:
+                        lines = []
+                        for line in fin:
+                            lines.append(line)
+                            if len(lines) >= batch_lines:
+                                break
+                        if not lines:
+                            break
+                        text = b"".join(lines).decode("latin-1")
+                        stop = any(ln.rstrip(b"\n") == b"@" for ln in lines)     # RNALfold stops reading at '@'
+                        fout.write(self.fold_text_bytes(text, span, encoding="latin-1"))
+                        if stop:
+                            break
+                os.rename(tmp, outname)   # atomic, like MP:3098
+            finally:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
         return list(outnames)

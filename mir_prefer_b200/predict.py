@@ -16,6 +16,8 @@ rows 6-9) are outside the hot path: they are injected as callables with the refe
 so the unmodified reference functions plug in.
 """
 
+from .fold import DUPLEX_EXCEPTION
+
 PASSED, FAILED = "PASSED", "FAILED"
 
 
@@ -48,7 +50,11 @@ class DuplexTable:
         self._table = dict(zip(keys, mf.duplex(queries))) if queries else {}
 
     def __call__(self, ss, mature, foldstart, foldend, regionstart, regionend, strand):
-        return self._table[(ss, mature[0], mature[1], foldstart, regionstart, regionend, strand)]
+        v = self._table[(ss, mature[0], mature[1], foldstart, regionstart, regionend, strand)]
+        if v == DUPLEX_EXCEPTION:
+            # the table answers the superset of pairs; only a pair the reference really asks for may raise like it
+            raise KeyError("get_maturestar_info: unbalanced structure around the mature (the reference raises here)")
+        return v
 
 
 def check_loci(structures, matures, region, dict_mapinfo_region, which, samplenames, allow_3nt_overhang, allow_no_star,

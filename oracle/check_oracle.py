@@ -15,7 +15,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
-from corpus import lcg_records, records_to_fasta, synth_loci  # noqa: E402
+from mir_prefer_b200.corpus import lcg_records, records_to_fasta, synth_loci  # noqa: E402
 
 ORACLE = os.path.join(HERE, "_build", "lfold_oracle")
 RLF = os.path.join(HERE, "_ref", "RNALfold")

@@ -62,6 +62,8 @@ def maturestar(ss, mature, foldstart, regionstart, regionend, strand):
     prime5 = bool(n_open)
     arm = [k for k in range(lo, hi) if ss[k] == sym]
     firstbp, lastbp = arm[0], arm[-1]
+    if partner[lastbp] < 0 or partner[firstbp] < 0:
+        raise KeyError("unmatched bracket in the mature (dict_bp[...] of MP:1932-1933)")
     star_start = partner[lastbp] - (l1 - 1 - lastbp) + 2
     star_end = partner[firstbp] + (firstbp - l0) + 3
     if l0 <= star_start:
@@ -75,6 +77,8 @@ def maturestar(ss, mature, foldstart, regionstart, regionend, strand):
         if star_start < 0:
             return FAIL_NAMES[6]
     inner = [k for k in arm if k < l1 - 2]
+    if not inner or partner[inner[-1]] < 0:
+        raise KeyError("dict_bp[mend] of MP:1949")
     mend = inner[-1]
     sstart, send = partner[mend], partner[firstbp]
     md = ss[l0:mend + 1]
@@ -95,7 +99,7 @@ def maturestar(ss, mature, foldstart, regionstart, regionend, strand):
         if ch == oc:
             st.append(k)
         elif ch == cc:
-            pairs[st.pop()] = k
+            pairs[st.pop()] = k      # IndexError where the reference's stat_duplex pops an empty list
     keys = sorted(pairs)
     n_loops = n_bulges = tot_loop = max_bulge = 0
     for a, b in zip(keys, keys[1:]):

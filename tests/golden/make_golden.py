@@ -16,7 +16,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
-from corpus import lcg_records, records_to_fasta, synth_loci  # noqa: E402
+from mir_prefer_b200.corpus import lcg_records, records_to_fasta, synth_loci  # noqa: E402
 
 RLF = "/root/reference/dependency/Linux/x64/RNALfold"
 

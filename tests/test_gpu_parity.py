@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from conftest import GOLDEN, golden_cases
-from corpus import lcg_records, records_to_fasta, synth_loci
+from mir_prefer_b200.corpus import lcg_records, records_to_fasta, synth_loci
 
 pytestmark = pytest.mark.gpu
 
@@ -292,13 +292,176 @@ def test_device_resident_entry_counts_match(mf):
         assert dev.nhits == nh and dev.ss_bytes == nb and not dev.downloaded
 
 
+def _records(res, n):
+    return [(res.hits(r), res.total(r)) for r in range(n)]
+
+
 def test_multi_device_sharding_matches_single(mf):
+    """One context over several devices (LPT shards, one host thread per device, downloads straight into the shared
+    result buffers) == the single-device result.  On a 1-GPU box the same ordinal is opened twice: two independent
+    pipelines on one GPU run exactly the multi-device host path."""
     import torch
     import mir_prefer_b200 as mp
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs >= 2 GPUs")
-    seqs = synth_loci(41, 300, "parity")
-    with mf.fold(seqs, 300) as a, mp.MirFold(devices=list(range(torch.cuda.device_count()))) as m2, m2.fold(seqs, 300) as b:
-        assert b.stats["n_devices"] >= 2
-        for r in range(len(seqs)):
-            assert a.hits(r) == b.hits(r) and a.total(r) == b.total(r)
+    ng = torch.cuda.device_count()
+    devices = list(range(ng)) if ng >= 2 else [0, 0]
+    seqs = synth_loci(41, 300, "parity") + ["", "ACG", "GGGAAACCC"] + synth_loci(42, 6, (700, 1500))
+    with mf.fold(seqs, 300) as a:
+        want = _records(a, len(seqs))
+    with mp.MirFold(devices=devices) as m2, m2.fold(seqs, 300) as b:
+        assert b.stats["n_devices"] == len(devices) and b.nhits == sum(len(h) for h, _ in want)
+        assert _records(b, len(seqs)) == want
+        _check_structure_properties(b, np.array([len(s) for s in seqs]), 300)
+    # several chunks per device and both lanes in flight on every device
+    os.environ["MIRFOLD_MEM_BUDGET_MB"] = "24"
+    try:
+        with mp.MirFold(devices=devices + [0]) as m3, m3.fold(seqs, 300) as c:
+            assert c.stats["n_devices"] == len(devices) + 1 and c.stats["n_chunks"] >= 2 * len(devices)
+            assert _records(c, len(seqs)) == want
+    finally:
+        del os.environ["MIRFOLD_MEM_BUDGET_MB"]
+
+
+def test_result_buffer_overflow_path(mf):
+    """The shared result buffers are sized from an estimate; chunks that do not fit take the overflow path and the
+    result is rebuilt once at exact size.  MIRFOLD_RESULT_CAP_SCALE shrinks the estimate to force it."""
+    import mir_prefer_b200 as mp
+    seqs = synth_loci(43, 120, (200, 420))
+    with mf.fold(seqs, 300) as a:
+        want = _records(a, len(seqs))
+    os.environ["MIRFOLD_MEM_BUDGET_MB"] = "16"
+    try:
+        for scale in ("0.0", "0.3"):     # nothing fits / the first chunks fit, the rest overflows
+            os.environ["MIRFOLD_RESULT_CAP_SCALE"] = scale
+            with mp.MirFold(devices=[0, 0]) as m2, m2.fold(seqs, 300) as b:
+                assert b.stats["n_chunks"] >= 4
+                assert _records(b, len(seqs)) == want
+                _check_structure_properties(b, np.array([len(s) for s in seqs]), 300)
+    finally:
+        del os.environ["MIRFOLD_MEM_BUDGET_MB"]
+        os.environ.pop("MIRFOLD_RESULT_CAP_SCALE", None)
+
+
+def test_serial_flag_and_lanes_give_identical_results(mf):
+    from mir_prefer_b200.fold import FLAG_SERIAL
+    import mir_prefer_b200 as mp
+    seqs = synth_loci(44, 200, "arabidopsis")
+    os.environ["MIRFOLD_MEM_BUDGET_MB"] = "64"
+    try:
+        with mp.MirFold() as m, m.fold(seqs, 300) as a, m.fold(seqs, 300, flags=FLAG_SERIAL) as b:
+            assert a.stats["n_chunks"] >= 3 and b.stats["n_chunks"] >= 2
+            assert _records(a, len(seqs)) == _records(b, len(seqs))
+    finally:
+        del os.environ["MIRFOLD_MEM_BUDGET_MB"]
+
+
+def test_streamed_chunks_equal_whole_result(mf, oracle):
+    """mirfold_fold_stream: every input record arrives in exactly one chunk, with the hits mirfold_fold returns;
+    records shorter than 5 nt arrive in the final hit-less chunk; an exception in the callback aborts the fold."""
+    import mir_prefer_b200 as mp
+    seqs = synth_loci(45, 150, (60, 420)) + ["", "ACGU", "GGGGAAAACCCC"] + synth_loci(46, 3, (800, 1200))
+    buf, off = mf.pack(seqs)
+    with mf.fold_packed(buf, off, 300) as a:
+        want = _records(a, len(seqs))
+    os.environ["MIRFOLD_MEM_BUDGET_MB"] = "16"
+    try:
+        with mp.MirFold(devices=[0, 0]) as m2:
+            got, devices = {}, set()
+
+            def on_chunk(ch):
+                devices.add(ch.device)
+                for k, r in enumerate(ch.records.tolist()):
+                    assert r not in got
+                    got[r] = (ch.hits(k), int(ch.total_mfe_dcal[k]))
+
+            st = m2.fold_stream(buf, off, 300, on_chunk)
+            assert st["n_chunks"] >= 4 and -1 in devices
+            assert [got[r] for r in range(len(seqs))] == want
+            o = oracle.fold(seqs[7], 300)
+            assert got[7] == (o["hits"], o["total"])
+
+            def boom(ch):
+                raise ValueError("stop")
+
+            with pytest.raises(ValueError):
+                m2.fold_stream(buf, off, 300, boom)
+            with m2.fold_packed(buf, off, 300) as again:          # the context is still usable afterwards
+                assert _records(again, len(seqs)) == want
+    finally:
+        del os.environ["MIRFOLD_MEM_BUDGET_MB"]
+
+
+def test_resident_batch_matches_host_path(mf):
+    """mirfold_batch_upload / mirfold_batch_fold: sequences resident in HBM on every device of the context."""
+    import mir_prefer_b200 as mp
+    seqs = synth_loci(47, 160, "arabidopsis") + ["", "ACG"]
+    buf, off = mf.pack(seqs)
+    with mf.fold_packed(buf, off, 300) as a:
+        want = _records(a, len(seqs))
+        nh, nb = a.nhits, a.ss_bytes
+    with mp.MirFold(devices=[0, 0]) as m2, m2.upload(buf, off, 300) as batch:
+        with batch.fold(download=False) as dev:
+            assert dev.nhits == nh and dev.ss_bytes == nb and not dev.downloaded and dev.stats["n_devices"] == 2
+        with batch.fold(download=True) as host:
+            assert _records(host, len(seqs)) == want
+
+
+def test_result_may_outlive_its_context():
+    """mirfold_close() with live results defers the context's deletion (use-after-free)."""
+    import gc
+    import mir_prefer_b200 as mp
+    seqs = synth_loci(48, 20, (100, 300))
+    m = mp.MirFold()
+    r1, r2 = m.fold(seqs, 300), m.fold(seqs[:5], 300)
+    want = _records(r1, len(seqs))
+    m.close()
+    assert _records(r1, len(seqs)) == want       # the pinned buffers belong to the result
+    r1.close()
+    del r2
+    gc.collect()
+    with pytest.raises(mp.MirfoldError):
+        m.fold(seqs, 300)
+
+
+def test_bad_offsets_are_rejected(mf):
+    import mir_prefer_b200 as mp
+    buf = np.frombuffer(b"ACGUACGUACGU", np.uint8)
+    with pytest.raises(mp.MirfoldError):
+        mf.fold_packed(buf, np.array([0, 8, 4, 12], np.uint64), 300)
+
+
+def test_fold_fasta_files_matches_golden_and_leaves_no_partial_file(mf, tmp_path, monkeypatch):
+    """fold_use_RNALfold() replacement (MP:3047-3119): one output file per shard, byte-identical to RNALfold's, folded
+    in line batches; CRLF / non-ASCII header bytes are echoed unchanged; a failing shard leaves neither the output nor
+    a .tmp file behind (the reference only renames a completed shard, MP:3098)."""
+    import mir_prefer_b200 as mp
+    names = [("synth8", 300), ("edge", 300)]
+    fas, outs = [], []
+    for k, (name, L) in enumerate(names):
+        fas.append(os.path.join(GOLDEN, name + ".in"))
+        outs.append(str(tmp_path / ("x_rnalfoldoutput_%d" % k)))
+    assert mf.fold_fasta_files(fas, outs, 300, batch_lines=5) == outs
+    for (name, L), out in zip(names, outs):
+        assert open(out, "rb").read() == open(os.path.join(GOLDEN, "%s.L%d.out" % (name, L)), "rb").read()
+    assert sorted(os.listdir(tmp_path)) == ["x_rnalfoldoutput_0", "x_rnalfoldoutput_1"]
+    # raw bytes in header lines
+    odd = tmp_path / "odd.fa"
+    odd.write_bytes(b">loc\xe9 1\r\nGGGGAAAACCCC\n>b\rc\nACGUACGUAC\n")
+    mf.fold_fasta_files([str(odd)], [str(tmp_path / "odd.out")], 300)
+    got = (tmp_path / "odd.out").read_bytes()
+    assert got.startswith(b">loc\xe9 1\r\n") and b">b\rc\n" in got
+    # failure in the second batch of the second shard
+    calls = {"n": 0}
+    real = mp.MirFold.fold_text_bytes
+
+    def flaky(self, text, span, encoding=None):
+        calls["n"] += 1
+        if calls["n"] == 3:
+            raise mp.MirfoldError(-2, "injected")
+        return real(self, text, span, encoding)
+
+    monkeypatch.setattr(mp.MirFold, "fold_text_bytes", flaky)
+    outs2 = [str(tmp_path / "y_0"), str(tmp_path / "y_1")]
+    with pytest.raises(mp.MirfoldError):
+        mf.fold_fasta_files(fas, outs2, 300, batch_lines=10)
+    left = sorted(f for f in os.listdir(tmp_path) if f.startswith("y_"))
+    assert left in ([], ["y_0"]) and not any(f.endswith(".tmp") for f in os.listdir(tmp_path))

@@ -6,7 +6,7 @@ import os
 import pytest
 
 from conftest import GOLDEN, golden_cases
-from corpus import lcg_records, records_to_fasta
+from mir_prefer_b200.corpus import lcg_records, records_to_fasta
 
 
 @pytest.mark.parametrize("name,L", golden_cases())
@@ -31,7 +31,7 @@ def test_oracle_matches_reference_binary_when_present(oracle):
     """Where oracle/_ref/RNALfold (the reference's own binary) is staged, compare live."""
     if not oracle.have_rlf():
         pytest.skip("oracle/_ref/RNALfold not staged")
-    from corpus import synth_loci
+    from mir_prefer_b200.corpus import synth_loci
     text = records_to_fasta([("s%d" % k, s) for k, s in enumerate(synth_loci(77, 6, (60, 340)))])
     assert oracle.fold_text(text, 300) == oracle.fold_text(text, 300, binary=oracle.RLF)
 

@@ -136,7 +136,7 @@ def test_predict_consumer_with_device_duplex_table(mf, predict_cases):
 def test_fold_records_equals_text_pipeline(mf, oracle, tmp_path):
     """Records -> device -> structure tuples == records -> FASTA -> RNALfold text -> reference-format parser;
     the RNALfold text itself is byte-identical to the oracle's for the shard the reference would write."""
-    from corpus import synth_loci
+    from mir_prefer_b200.corpus import synth_loci
     seqs = synth_loci(31, 10, (120, 330)) + ["", "ACGTNNacgtACGTTGCA"]
     recs = []
     for k, s in enumerate(seqs):

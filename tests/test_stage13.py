@@ -174,6 +174,35 @@ def test_classifier_error_behaviour_matches_reference():
         S.filter_ss("())")               # reference: pop from empty list
 
 
+@pytest.fixture(scope="module")
+def stage3b():
+    return json.load(open(os.path.join(GOLDEN, "stage3b.json")))
+
+
+def _oracle_verdict(D, q):
+    try:
+        return D.maturestar(*q)
+    except (KeyError, IndexError):
+        return "EXCEPTION"
+
+
+def test_duplex_oracle_matches_rare_branch_fixture(stage3b):
+    """CPU: every FAIL_* branch incl. MATCHED_BASES, TOO_MANY_BULGE_OR_LOOP, TOTAL_LOOP_SIZE and the inputs on which
+    the reference raises (tests/golden/make_golden_stage3b.py, the reference's own get_maturestar_info)."""
+    import duplex_oracle as D
+    from collections import Counter
+    st = stage3b["structures"]
+    seen = Counter()
+    for q in stage3b["queries"]:
+        got = _oracle_verdict(D, (st[q["ss"]], q["mature"], q["fold_start"], q["region"][0], q["region"][1], q["strand"]))
+        want = q["result"] if isinstance(q["result"], str) else tuple(q["result"])
+        assert got == want
+        seen[want if isinstance(want, str) else "PASS"] += 1
+    for name in ("FAIL_STRUCTURE_MATCHED_BASES", "FAIL_STRUCTURE_TOO_MANY_BULGE_OR_LOOP", "FAIL_STRUCTURE_TOTAL_LOOP_SIZE_LARGER_THAN_5",
+                 "FAIL_STRUCTURE_MAX_BULGE_LARGE_THAN_2", "FAIL_STRUCTURE_NUM_BULGE_MORE_THAN_2", "EXCEPTION"):
+        assert seen[name] >= 20, (name, seen[name])
+
+
 def test_duplex_oracle_matches_reference_fixture(stage3):
     """CPU: the duplex restatement (oracle) against the reference's own outputs."""
     import duplex_oracle as D
@@ -270,7 +299,7 @@ def test_structures_from_result_equals_file_parser(mf, tmp_path):
 @pytest.mark.gpu
 def test_native_classifier_at_scale(mf):
     """mirfold_classify() vs the Python rules on 600 folded loci (threaded path, > 256 records)."""
-    from corpus import synth_loci
+    from mir_prefer_b200.corpus import synth_loci
     seqs = synth_loci(77, 600, "parity")
     headers = [">c:%d-%d + 1-22 0 1,22,+" % (k, k + len(s)) for k, s in enumerate(seqs)]
     with mf.fold(seqs, 300) as res:
@@ -290,11 +319,23 @@ def test_duplex_kernel_matches_reference_fixture(mf, stage3):
 
 
 @pytest.mark.gpu
+def test_duplex_kernel_matches_rare_branch_fixture(mf, stage3b):
+    """k_duplex on the rare verdicts and on unbalanced input: code 100 exactly where the reference raises."""
+    from mir_prefer_b200.fold import DUPLEX_EXCEPTION
+    st = stage3b["structures"]
+    qs = [(st[q["ss"]], q["mature"], q["fold_start"], q["region"][0], q["region"][1], q["strand"]) for q in stage3b["queries"]]
+    got = mf.duplex(qs)
+    for g, q in zip(got, stage3b["queries"]):
+        want = q["result"] if isinstance(q["result"], str) else tuple(q["result"])
+        assert g == (DUPLEX_EXCEPTION if want == "EXCEPTION" else want)
+
+
+@pytest.mark.gpu
 def test_duplex_kernel_matches_oracle_on_fresh_folds(mf):
     """All (structure x mature) pairs of freshly folded loci: device verdicts == oracle restatement."""
     import numpy as np
     import duplex_oracle as D
-    from corpus import synth_loci
+    from mir_prefer_b200.corpus import synth_loci
     seqs = synth_loci(55, 24, "arabidopsis")
     rng = np.random.default_rng(8)
     qs = []

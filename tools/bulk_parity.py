@@ -13,7 +13,7 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
-from corpus import synth_loci  # noqa: E402
+from mir_prefer_b200.corpus import synth_loci  # noqa: E402
 import mir_prefer_b200 as mp  # noqa: E402
 
 law = sys.argv[1] if len(sys.argv) > 1 else "parity"

@@ -2,7 +2,7 @@ import sys, time
 import os; R=os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, R); sys.path.insert(0, R+'/oracle')
 import numpy as np
 import oracle as O
-from corpus import synth_loci, lcg_records
+from mir_prefer_b200.corpus import synth_loci, lcg_records
 import mir_prefer_b200 as mp
 mf = mp.MirFold()
 print(mp._lib.load().mirfold_version())

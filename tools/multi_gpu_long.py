@@ -7,7 +7,7 @@ import time
 
 sys.path.insert(0, "."); sys.path.insert(0, "oracle")
 import torch
-from corpus import synth_loci
+from mir_prefer_b200.corpus import synth_loci
 import mir_prefer_b200 as mp
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 8000

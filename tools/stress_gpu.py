@@ -2,7 +2,7 @@ import sys, time
 sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/oracle")
 import numpy as np
 import oracle as O
-from corpus import synth_loci
+from mir_prefer_b200.corpus import synth_loci
 import mir_prefer_b200 as mp
 O.build()
 mf = mp.MirFold()

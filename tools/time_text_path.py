@@ -1,6 +1,6 @@
 import sys, time
 sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/oracle")
-from corpus import synth_loci
+from mir_prefer_b200.corpus import synth_loci
 import mir_prefer_b200 as mp
 seqs = synth_loci(1001, 10000, "parity")
 text = "".join(">locus%d:%d-%d + 1-22 0 1,22,+\n%s\n" % (k, 1, len(s) + 1, s) for k, s in enumerate(seqs))
