@@ -51,7 +51,7 @@ def workload_packed(rank, nloci, name=None):
     """(uint8 buffer, uint64 offsets) of the workload; the generator is a sequential Python loop (30 s for 200 k
     loci), so the packed corpus is cached under the temp dir for the back-to-back runs of a scaling sweep."""
     law, seed, _ = WORKLOADS[name or WORKLOAD]
-    fn = os.path.join(tempfile.gettempdir(), "mirfold_corpus_%s_%d_%d.npz" % (law, seed + rank, nloci))
+    fn = os.path.join(os.environ.get("MIRFOLD_CORPUS_DIR") or tempfile.gettempdir(), "mirfold_corpus_%s_%d_%d.npz" % (law, seed + rank, nloci))
     try:
         z = np.load(fn)
         return z["buf"], z["off"]

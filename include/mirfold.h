@@ -244,6 +244,51 @@ int mirfold_duplex(mirfold_ctx *ctx, const char *ss_arena, uint64_t ss_bytes,
                    mirfold_duplex_verdict *verdicts /* nq entries, caller-allocated */);
 const char *mirfold_duplex_fail_name(int code);
 
+/* ---- stages 1 + 3 fused on the device after traceback ----
+ * Replaces, in one call: the fold (miR_PREFeR.py:3064), the candidate-structure pass of
+ * get_structures_next_extendregion (:1566-1589) and get_maturestar_info (:1876-1999) for every (candidate structure x
+ * size-admissible mature) pair of every record -- the superset of pairs check_loci (:2246-2262) can ask for.  The hit
+ * text never leaves the device: only the candidate structures, their dot-bracket strings and the verdicts are
+ * downloaded.  Records are what dump_piece writes (:1124-1143): the region [start, end) and the "M:s-e/strand/depth"
+ * matures of the header line.
+ *   regions[r]                      region of record r (genome coordinates)
+ *   matures[mature_off[r] .. mature_off[r+1])   its matures, in header order
+ * Output (owned by the library until mirfold_free_candidates):
+ *   structures of record r: structs[struct_begin[r] .. +struct_count[r]) in the reference's order; ss_off indexes ss_arena
+ *   (NUL-terminated strings); verdicts of structure s: verdicts[verdict_begin[s] .. +verdict_count[s]), one per mature
+ *   with min_mature_len <= end-start <= max_mature_len in header order; verdict_mature[v] = index of that mature inside
+ *   the record's mature list.  Returns MIRFOLD_ERR_ARG for input on which the reference's classifier raises. */
+typedef struct mirfold_mature {
+    int32_t start, end;   /* genome coordinates [start, end)                         */
+    int32_t strand;       /* '+' or '-' (the strand get_maturestar_info is called with) */
+    int32_t depth;        /* carried through for the caller                          */
+} mirfold_mature;
+typedef struct mirfold_region {
+    int32_t start, end;   /* extended region [start, end) of the record              */
+} mirfold_region;
+typedef struct mirfold_candidates {
+    uint32_t nseq;
+    uint32_t reserved;
+    uint64_t nstructs;
+    const uint64_t *struct_begin;       /* nseq */
+    const uint32_t *struct_count;       /* nseq */
+    const mirfold_structure *structs;
+    const char *ss_arena;
+    uint64_t ss_bytes;
+    uint64_t nverdicts;
+    const uint64_t *verdict_begin;      /* nstructs */
+    const uint32_t *verdict_count;      /* nstructs */
+    const mirfold_duplex_verdict *verdicts;
+    const uint32_t *verdict_mature;     /* nverdicts */
+    uint64_t nhits;                     /* hairpins folded (not downloaded) */
+    mirfold_stats stats;
+} mirfold_candidates;
+int mirfold_fold_candidates(mirfold_ctx *ctx, const char *seqs, const uint64_t *seq_off, uint32_t nseq, int span_L,
+                            uint32_t flags, const mirfold_region *regions, const mirfold_mature *matures,
+                            const uint64_t *mature_off, int minlen, int minloop, int min_mature_len, int max_mature_len,
+                            mirfold_candidates **out);
+void mirfold_free_candidates(mirfold_candidates *c);
+
 #ifdef __cplusplus
 }
 #endif

@@ -67,12 +67,29 @@ class DuplexVerdict(C.Structure):
                 ("total_dots", C.c_int32), ("total_bps", C.c_int32)]
 
 
+class Mature(C.Structure):
+    _fields_ = [("start", C.c_int32), ("end", C.c_int32), ("strand", C.c_int32), ("depth", C.c_int32)]
+
+
+class Region(C.Structure):
+    _fields_ = [("start", C.c_int32), ("end", C.c_int32)]
+
+
+class Candidates(C.Structure):
+    _fields_ = [("nseq", C.c_uint32), ("reserved", C.c_uint32), ("nstructs", C.c_uint64),
+                ("struct_begin", C.POINTER(C.c_uint64)), ("struct_count", C.POINTER(C.c_uint32)),
+                ("structs", C.POINTER(Structure)), ("ss_arena", C.c_void_p), ("ss_bytes", C.c_uint64),
+                ("nverdicts", C.c_uint64), ("verdict_begin", C.POINTER(C.c_uint64)), ("verdict_count", C.POINTER(C.c_uint32)),
+                ("verdicts", C.POINTER(DuplexVerdict)), ("verdict_mature", C.POINTER(C.c_uint32)), ("nhits", C.c_uint64),
+                ("stats", Stats)]
+
+
 # every symbol include/mirfold.h declares
 EXPORTS = ["mirfold_open", "mirfold_close", "mirfold_fold", "mirfold_fold_device", "mirfold_debug_matrices",
            "mirfold_free_result", "mirfold_strerror", "mirfold_last_error", "mirfold_version", "mirfold_duplex",
            "mirfold_duplex_fail_name", "mirfold_int_peak", "mirfold_format_records", "mirfold_free_text",
            "mirfold_classify", "mirfold_free_structures", "mirfold_fold_stream", "mirfold_batch_upload", "mirfold_batch_fold",
-           "mirfold_batch_free", "mirfold_plan_shards", "mirfold_int_peak2"]
+           "mirfold_batch_free", "mirfold_plan_shards", "mirfold_int_peak2", "mirfold_fold_candidates", "mirfold_free_candidates"]
 
 _lib = None
 
@@ -137,5 +154,14 @@ def load():
     lib.mirfold_plan_shards.argtypes = [C.POINTER(C.c_uint64), C.c_uint32, C.c_int, C.c_int, C.POINTER(C.c_uint32),
                                         C.POINTER(C.c_uint64)]
     lib.mirfold_plan_shards.restype = C.c_int
+    if os.environ.get("MIRFOLD_LIB_PATH") and not hasattr(lib, "mirfold_fold_candidates"):
+        _lib = lib      # an older A/B build of the library: the entry points below are not in it
+        return lib
+    lib.mirfold_fold_candidates.argtypes = [vp, C.c_void_p, C.POINTER(C.c_uint64), C.c_uint32, C.c_int, C.c_uint32, C.c_void_p,
+                                            C.c_void_p, C.POINTER(C.c_uint64), C.c_int, C.c_int, C.c_int, C.c_int,
+                                            C.POINTER(C.POINTER(Candidates))]
+    lib.mirfold_fold_candidates.restype = C.c_int
+    lib.mirfold_free_candidates.argtypes = [C.POINTER(Candidates)]
+    lib.mirfold_free_candidates.restype = None
     _lib = lib
     return lib

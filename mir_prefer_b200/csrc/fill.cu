@@ -198,14 +198,21 @@ __device__ __forceinline__ void dev_phase_a(const int *Mb, int *rD, StrideT NS, 
 }
 
 
-// phase A on 16-bit row pairs (narrow kernel).  Mp holds fML16 twice per diagonal, as two compact
-// arrays of NS/2 words: E[t] = rows (2t+1 | 2t+2) and O[t] = rows (2t+2 | 2t+3) (lo | hi half).
-// Thread t owns the rows (i, i+1) = (2t+1, 2t+2): the left operand fML(i,i+e) | fML(i+1,i+1+e) is
-// E[t] of diagonal e, the right operand fML(i+e+1, .) | fML(i+e+2, .) is O[t + e/2] (e even) or
-// E[t + (e+1)/2] (e odd), so a warp always reads 32 consecutive words and one LDG + one
-// VIADDMNMX.S16x2 covers two split terms.  Values are exact while every finite fML of the locus
+// phase A on 16-bit row pairs (narrow kernel).  Mp holds fML16 per diagonal as words of two rows: E[t] = rows
+// (2t+1 | 2t+2) (lo | hi half).  Thread t owns the rows (i, i+1) = (2t+1, 2t+2): the left operand
+// fML(i,i+e) | fML(i+1,i+1+e) is E[t] of diagonal e.  The right operand fML(i+e+1, .) | fML(i+e+2, .) is E[t + (e+1)/2]
+// for odd e; for even e it is the odd-aligned pair rows (2u+2 | 2u+3), u = t + e/2.  Two layouts (template OC):
+//   OC = true  : a second, odd-aligned copy O[u] of every diagonal is stored behind E (NS words per diagonal) -- one LDG;
+//   OC = false : E only (NS/2 words per diagonal); the pair is spliced from E[u] and the neighbouring lane's E[u+1]
+//                (SHFL + PRMT, one more halo lane).
+// Measured (profiles/r02_v2_fml16_layout_ab.txt): the single copy cuts the kernel's DRAM traffic by a third (17.9 -> 11.6 GB
+// per 20 k loci) and wins 6 % where the strips' working set overflows L2 (stride-608 tiles: long loci, L = 500), but the
+// extra SHFL in the dependent chain costs 4.5 % where it already fits (stride <= 352), so the layout is a bucket property.
+// One LDG + one VIADDMNMX.S16x2 covers two split terms.  Values are exact while every finite fML of the locus
 // stays above MF16M_GUARD (fML16 INF = 16383: INF+INF and INF+finite stay above MF16M_VALID and
 // never wrap); otherwise the locus is flagged for the 32-bit kernel.
+// ---- OC = true: the round-1 functions, kept verbatim (the templated form below compiles to a 5 % slower stride-352 kernel
+// for reasons that are ptxas' own: same-box A/B 139.6 vs 132.3 ms on 40 k arabidopsis loci) ----
 template <class StrideT>
 __device__ __forceinline__ void dev_store_fml16(unsigned int *Mp, StrideT NS, int d, int i, int m, int *sFlag)
 {
@@ -217,6 +224,8 @@ __device__ __forceinline__ void dev_store_fml16(unsigned int *Mp, StrideT NS, in
     if (i >= 2) row[NS + i - 2] = (unsigned short)m16;
 }
 
+// non-systolic strips of the two-copy layout (MIRFOLD_OPTS bit 2; kept because removing this cold path costs the
+// stride-352 kernel 3 % -- code placement, measured same-box)
 template <int NT, class StrideT>
 __device__ __forceinline__ void dev_phase_a16(const unsigned int *Mp, int *rD, StrideT NS, int n, int d, int d1,
                                               int tid, bool prefetch)
@@ -339,14 +348,6 @@ __device__ __forceinline__ void dev_phase_a16_sys(const unsigned int *Mp, int *r
         }
         pa += 2 * NS;
         pb += -2 * NS + 1;
-#ifndef MF_SYS_PF
-#define MF_SYS_PF 0   /* L1 prefetch distance of the strip operands in steps (even); 0 = none */
-#endif
-#if MF_SYS_PF > 0
-#define MF_SYS_PREFETCH(a_, b_) if (e + MF_SYS_PF + 1 <= emain) { dev_prefetch_l1(a_); dev_prefetch_l1(b_); }
-#else
-#define MF_SYS_PREFETCH(a_, b_)
-#endif
 #define MF_SYS_COMPUTE(V0, V1, V2, P0, AV, N0)                                                     \
     {                                                                                              \
         const unsigned int av = (AV), n0 = (N0);                                                   \
@@ -366,32 +367,6 @@ __device__ __forceinline__ void dev_phase_a16_sys(const unsigned int *Mp, int *r
 #endif
 #define MF_PRAGMA_(x) _Pragma(#x)
 #define MF_UNROLL_(n) MF_PRAGMA_(unroll n)
-#ifdef MF_SYS_PIPE
-        // software pipeline: the eight words of the NEXT four steps are requested before the current four are
-        // consumed, so one L2 round trip overlaps ~55 instructions of shuffles and min-plus instead of preceding them
-        if (e + 7 <= emain) {
-            unsigned int q0 = pa[0], q1 = pb[0], q2 = pa[NS], q3 = pb[-NS - H + 1];
-            unsigned int q4 = pa[2 * NS], q5 = pb[-2 * NS + 1], q6 = pa[3 * NS], q7 = pb[-3 * NS - H + 2];
-            for (; e + 7 <= emain; e += 4) {
-                pa += 4 * NS;
-                pb += -4 * NS + 2;
-                const unsigned int r0 = pa[0], r1 = pb[0], r2 = pa[NS], r3 = pb[-NS - H + 1];
-                const unsigned int r4 = pa[2 * NS], r5 = pb[-2 * NS + 1], r6 = pa[3 * NS], r7 = pb[-3 * NS - H + 2];
-                MF_SYS_COMPUTE(X0, X1, X2, Y0, q0, q1)
-                MF_SYS_COMPUTE(Y0, Y1, Y2, X0, q2, q3)
-                MF_SYS_COMPUTE(X0, X1, X2, Y0, q4, q5)
-                MF_SYS_COMPUTE(Y0, Y1, Y2, X0, q6, q7)
-                q0 = r0; q1 = r1; q2 = r2; q3 = r3; q4 = r4; q5 = r5; q6 = r6; q7 = r7;
-            }
-            MF_SYS_COMPUTE(X0, X1, X2, Y0, q0, q1)
-            MF_SYS_COMPUTE(Y0, Y1, Y2, X0, q2, q3)
-            MF_SYS_COMPUTE(X0, X1, X2, Y0, q4, q5)
-            MF_SYS_COMPUTE(Y0, Y1, Y2, X0, q6, q7)
-            e += 4;
-            pa += 4 * NS;
-            pb += -4 * NS + 2;
-        }
-#endif
         MF_UNROLL_(MF_SYS_UNROLL)
         for (; e + 1 <= emain; e += 2) {
             MF_SYS_STEP(X0, X1, X2, Y0, 0, 0)
@@ -430,6 +405,153 @@ __device__ __forceinline__ void dev_phase_a16_sys(const unsigned int *Mp, int *r
             }
         }
     }
+}
+
+
+// ---- OC = false: single copy, spliced right operands ----
+template <bool OC, class StrideT>
+__device__ __forceinline__ void dev_store_fml16x(unsigned int *Mp, StrideT NS, int d, int i, int m, int *sFlag)
+{
+    const int m16 = (m >= MF_INF / 2) ? MF16M_INF : max(m, -32768);
+    if (m < MF16M_GUARD) *sFlag = 1;
+    unsigned short *row = (unsigned short *)(Mp + (d - 4) * (OC ? NS : NS / 2));
+    // halfword index inside E: i-1; inside O (after NS/2 words = NS halfwords): i-2
+    row[i - 1] = (unsigned short)m16;
+    if (OC && i >= 2) row[NS + i - 2] = (unsigned short)m16;
+}
+
+// Systolic strips.  The right operand of thread t at split e and strip
+// diagonal s is the word the next row pair t+1 used two splits earlier for diagonal s-2, so only
+// s = 0 is loaded; s = 1 is spliced from the previous step's s = 0 words of this lane and lane+1, and
+// s = 2..4 arrive by SHFL.DOWN from lane+1's registers of step e-2 (X*/Y* hold the words of the last
+// even/odd step).  2 LDG + 4 SHFL + 1 PRMT + 5 VIADDMNMX.S16x2 per step instead of 6 LDG + 5:
+// the strips are bound by L1-miss traffic, not by issue slots.  A warp covers 30 (OC) or 29 row pairs; the
+// remaining lanes are the halo that feeds the last ones and are recomputed by the next tile.
+template <int NT, bool OC, class StrideT>
+__device__ __forceinline__ void dev_phase_a16_sysx(const unsigned int *Mp, int *rD, StrideT NS, int n, int d, int d1, int tid)
+{
+    const int emax = d1 - 5;  // e ranges 4..emax for the widest diagonal of the strip
+    if (emax < 4) return;
+    constexpr int NW = NT / 32, TW = OC ? 30 : 29;
+    const int W = OC ? NS : NS / 2;                                  // words per diagonal
+    const int OH = OC ? NS / 2 : 0;                                  // offset of the odd-aligned copy inside a diagonal
+    const int R = n - d, RP = (R + 1) >> 1;
+    const int ntiles = (RP + TW - 1) / TW;
+    const int nparts = max(1, min(NW / ntiles, 8));
+    const int span = emax - 3;
+    const int per = ((span + nparts - 1) / nparts + 1) & ~1;      // even: every part starts at an even e
+    const int lane = tid & 31, wid = tid >> 5;
+    // rows (2u+2 | 2u+3): the stored copy, or spliced from the words u (this lane) and u+1 (lane+1)
+#define MF_ODDPAIR(p_) (OC ? *(p_) : __byte_perm(*(p_), __shfl_down_sync(0xffffffffu, *(p_), 1), 0x5432))
+    for (int unit = wid; unit < ntiles * nparts; unit += NW) {
+        const int part = unit / ntiles, tile = unit - part * ntiles;
+        const int e0 = 4 + part * per, e1 = min(emax, e0 + per - 1);
+        if (e0 > e1) continue;
+        const int t = tile * TW + lane, i = 2 * t + 1;              // rows i (lo half) and i+1 (hi half)
+        const int ns = min(d1 - d, n - d - i) + 1;                  // valid strip diagonals for row i (<= 0: none)
+        const int nsh = min(d1 - d, n - d - i - 1) + 1;             // ... and for row i+1
+        const unsigned int *pa = Mp + (e0 - 4) * W + t;                        // left: E[t] of diagonal e
+        const unsigned int *pb = Mp + (d - 5 - e0) * W + OH + t + (e0 >> 1);   // right, e even: pair u = t + e/2 of diagonal d-1-e   (+ s*W for d+s)
+        unsigned int a0 = MF16M_INF2, a1 = MF16M_INF2, a2 = MF16M_INF2, a3 = MF16M_INF2, a4 = MF16M_INF2;
+        const int emain = min(e1, d - 5);
+        unsigned int X0 = 0, X1 = 0, X2 = 0, Y0 = 0, Y1 = 0, Y2 = 0;
+        int e = e0;
+        // every term of the main range is valid for every strip diagonal the row has, and halves / diagonals a
+        // row does not have are simply not stored, so the accumulation is unconditional.
+        // prologue: two steps with all five words loaded
+        if (e <= emain) {
+            const unsigned int av = pa[0];
+            X0 = MF_ODDPAIR(pb); X1 = MF_ODDPAIR(pb + W); X2 = MF_ODDPAIR(pb + 2 * W);
+            const unsigned int x3 = MF_ODDPAIR(pb + 3 * W), x4 = MF_ODDPAIR(pb + 4 * W);
+            a0 = __viaddmin_s16x2(av, X0, a0); a1 = __viaddmin_s16x2(av, X1, a1); a2 = __viaddmin_s16x2(av, X2, a2);
+            a3 = __viaddmin_s16x2(av, x3, a3); a4 = __viaddmin_s16x2(av, x4, a4);
+            e++;
+        }
+        if (e <= emain) {
+            const unsigned int av = pa[W];
+            const unsigned int *q = pb - W - OH + 1;
+            Y0 = q[0]; Y1 = q[W]; Y2 = q[2 * W];
+            a0 = __viaddmin_s16x2(av, Y0, a0); a1 = __viaddmin_s16x2(av, Y1, a1); a2 = __viaddmin_s16x2(av, Y2, a2);
+            a3 = __viaddmin_s16x2(av, q[3 * W], a3); a4 = __viaddmin_s16x2(av, q[4 * W], a4);
+            e++;
+        }
+        pa += 2 * W;
+        pb += -2 * W + 1;
+#define MF_SYS_COMPUTE(V0, V1, V2, P0, AV, N0)                                                     \
+    {                                                                                              \
+        const unsigned int av = (AV), n0 = (N0);                                                   \
+        /* s = 1: rows (i, i+1) need the previous step's s = 0 words of rows (i+1, i+2) */         \
+        const unsigned int n1 = __byte_perm(P0, __shfl_down_sync(0xffffffffu, P0, 1), 0x5432);     \
+        const unsigned int b2 = __shfl_down_sync(0xffffffffu, V0, 1);                              \
+        const unsigned int b3 = __shfl_down_sync(0xffffffffu, V1, 1);                              \
+        const unsigned int b4 = __shfl_down_sync(0xffffffffu, V2, 1);                              \
+        a0 = __viaddmin_s16x2(av, n0, a0); a1 = __viaddmin_s16x2(av, n1, a1);                      \
+        a2 = __viaddmin_s16x2(av, b2, a2); a3 = __viaddmin_s16x2(av, b3, a3);                      \
+        a4 = __viaddmin_s16x2(av, b4, a4);                                                         \
+        V0 = n0; V1 = n1; V2 = b2;                                                                 \
+    }
+#ifndef MF_SYS_UNROLL
+#define MF_SYS_UNROLL 2
+#endif
+#define MF_PRAGMA_(x) _Pragma(#x)
+#define MF_UNROLL_(n) MF_PRAGMA_(unroll n)
+        MF_UNROLL_(MF_SYS_UNROLL)
+        for (; e + 1 <= emain; e += 2) {
+            MF_SYS_COMPUTE(X0, X1, X2, Y0, pa[0], MF_ODDPAIR(pb))          // even split
+            MF_SYS_COMPUTE(Y0, Y1, Y2, X0, pa[W], pb[-W - OH + 1])         // odd split
+            pa += 2 * W;
+            pb += -2 * W + 1;
+        }
+        if (e <= emain) {
+            MF_SYS_COMPUTE(X0, X1, X2, Y0, pa[0], MF_ODDPAIR(pb))
+            e++;
+        }
+#undef MF_SYS_COMPUTE
+        for (; e <= e1; e++) {   // tail: diagonal d+s accepts e <= d+s-5 (s >= 1 only), words loaded directly
+            const unsigned int av = Mp[(e - 4) * W + t];
+            const unsigned int *qe = Mp + (d - 5 - e) * W + t + ((e + 1) >> 1);   // E[t + ceil(e/2)] of diagonal d-1-e
+            // right operand of strip diagonal s_: E word (odd e), else the odd-aligned pair (stored copy or two E words)
+            auto right = [&](int s_) {
+                if (e & 1) return qe[s_ * W];
+                return OC ? qe[s_ * W + OH] : __byte_perm(qe[s_ * W], qe[s_ * W + 1], 0x5432);
+            };
+            if (e <= d + 1 - 5) a1 = __viaddmin_s16x2(av, right(1), a1);
+            if (e <= d + 2 - 5) a2 = __viaddmin_s16x2(av, right(2), a2);
+            if (e <= d + 3 - 5) a3 = __viaddmin_s16x2(av, right(3), a3);
+            a4 = __viaddmin_s16x2(av, right(4), a4);
+        }
+#undef MF_ODDPAIR
+        if (lane < TW) {
+            const unsigned int acc[5] = {a0, a1, a2, a3, a4};
+#pragma unroll
+            for (int s = 0; s < 5; s++) {
+                const int lo = (int)(short)(acc[s] & 0xffffu), hi = (int)acc[s] >> 16;
+                int *dst = &rD[((d + s) & (MF_RING_DML - 1)) * NS + (i - 1)];
+                if (s < ns && lo < MF16M_VALID) {
+                    if (nparts == 1) dst[0] = lo;
+                    else atomicMin(dst, lo);
+                }
+                if (s < nsh && hi < MF16M_VALID) {
+                    if (nparts == 1) dst[1] = hi;
+                    else atomicMin(dst + 1, hi);
+                }
+            }
+        }
+    }
+}
+
+
+template <bool OC, class StrideT>
+__device__ __forceinline__ void dev_store_fml16_sel(unsigned int *Mp, StrideT NS, int d, int i, int m, int *sFlag)
+{
+    if (OC) dev_store_fml16(Mp, NS, d, i, m, sFlag);
+    else dev_store_fml16x<false>(Mp, NS, d, i, m, sFlag);
+}
+template <int NT, bool OC, class StrideT>
+__device__ __forceinline__ void dev_phase_a16_sel(const unsigned int *Mp, int *rD, StrideT NS, int n, int d, int d1, int tid)
+{
+    if (OC) dev_phase_a16_sys<NT>(Mp, rD, NS, n, d, d1, tid);
+    else dev_phase_a16_sysx<NT, false>(Mp, rD, NS, n, d, d1, tid);
 }
 
 // ------------------------------------------------------------------------------------ K2 (shared-memory rings)
@@ -774,7 +896,16 @@ __global__ void __launch_bounds__(NT, MINB) k_fill_s16(FillLaunch a)
 
     int *Cb = a.C + L.band_off;
     int *Mb = a.M + L.band_off;
-    unsigned int *Mp = a.Mp + L.band_off;
+    constexpr bool OC = NS <= 352;           // fML16 layout of this bucket (see dev_store_fml16)
+#ifdef MF_NO_BULK_ROWS
+    constexpr bool BULK = false;
+#else
+    // int32 fML rows leave the SM as one cp.async.bulk per diagonal from the shared row buffer instead of one STG per cell.
+    // Same-box A/B (profiles/r02_v2_fml16_layout_ab.txt): neutral to slightly faster for the stride-608 bucket, 1.3 % slower
+    // for stride 352 (the single issuing thread's proxy fence + wait sit on the fML warps' critical path), so by bucket.
+    constexpr bool BULK = NS > 352;
+#endif
+    unsigned int *Mp = a.Mp + L.band_off;    // the single-copy layout uses the first half of the locus' words
     int *rD = a.ring + L.ring_off;   // [MF_RING_DML][NS]
     for (int k = tid; k < MF_RING_DML * NS; k += NT) rD[k] = MF_INF;
     __syncthreads();
@@ -798,8 +929,8 @@ __global__ void __launch_bounds__(NT, MINB) k_fill_s16(FillLaunch a)
         if (it >= 5 && (it - 5) % 5 == 0 && it - 1 <= dmax) {
             // DML strip [it-1, it+3]
             if (a.opts & 2) dev_phase_a<NT>(Mb, rD, NS, n, it - 1, min(it + 3, dmax), tid, !(a.opts & 1));
-            else if (a.opts & 4) dev_phase_a16<NT>(Mp, rD, NS, n, it - 1, min(it + 3, dmax), tid, !(a.opts & 1));
-            else dev_phase_a16_sys<NT>(Mp, rD, NS, n, it - 1, min(it + 3, dmax), tid);
+            else if (OC && (a.opts & 4)) dev_phase_a16<NT>(Mp, rD, NS, n, it - 1, min(it + 3, dmax), tid, !(a.opts & 1));
+            else dev_phase_a16_sel<NT, OC>(Mp, rD, NS, n, it - 1, min(it + 3, dmax), tid);
             TL_MARK(0)
             __syncthreads();
             TL_MARK(5)
@@ -879,14 +1010,17 @@ __global__ void __launch_bounds__(NT, MINB) k_fill_s16(FillLaunch a)
         } else {
             const int mt = tid - CT;
             const int dm = it - 1;
+            // the int32 fML row of diagonal it-2 (complete since the last barrier) leaves through the TMA engine
+            if (BULK && mt == 0 && dm - 1 >= 4)
+                dev_bulk_store_row(Mb + (dm - 5) * NS, sMrow + ((dm - 1) & 1) * NS, (unsigned)(((n - dm + 1) * 4 + 15) & ~15));
             if (dm >= 4) {
                 const int *Mprev = sMrow + ((dm - 1) & 1) * NS;
                 int *Mcur = sMrow + (dm & 1) * NS;
                 for (int i = mt + 1; i <= n - dm; i += MT) {
                     const int m = dev_fml16(P, sS, sS1, sPair, sB, RS, Mprev, rD, NS, i, dm, Ls);
-                    Mb[(dm - 4) * NS + i - 1] = m;
+                    if (!BULK) Mb[(dm - 4) * NS + i - 1] = m;
                     Mcur[i - 1] = m;
-                    dev_store_fml16(Mp, NS, dm, i, m, &sFlag);   // 16-bit copies for the DML strips
+                    dev_store_fml16_sel<OC>(Mp, NS, dm, i, m, &sFlag);   // 16-bit copy (copies) for the DML strips
                 }
             }
             TL_MARK(1)
@@ -914,10 +1048,15 @@ __global__ void __launch_bounds__(NT, MINB) k_fill_s16(FillLaunch a)
             }
         }
         TL_MARK(3)
+        if (BULK && tid == CT) dev_bulk_wait_read();   // the row buffer of diagonal it-2 is rewritten in the next iteration
         __syncthreads();
         TL_MARK(4)
     }
     TL_DUMP
+    if (BULK && tid == CT && dmax >= 4) {      // last row: diagonal dmax, filled in the final iteration
+        dev_bulk_store_row(Mb + (dmax - 4) * NS, sMrow + (dmax & 1) * NS, (unsigned)(((n - dmax) * 4 + 15) & ~15));
+        dev_bulk_wait_all();
+    }
     if (tid == 0 && sFlag) a.flags[blockIdx.x] = 1;
 }
 

@@ -63,3 +63,17 @@ __device__ __forceinline__ void dev_sts16x2(unsigned addr, int a, int b)
     asm volatile("st.shared.u16 [%0], %1;\n\tst.shared.u16 [%0+2], %2;" ::"r"(addr), "h"((unsigned short)a), "h"((unsigned short)b) : "memory");
 }
 __device__ __forceinline__ int dev_rtype(int t) { return t ? (((t - 1) ^ 1) + 1) : 0; }   // {0,2,1,4,3,6,5}
+
+// ---- bulk asynchronous copies (TMA engine, 1-D): a finished band row leaves the SM as ONE cp.async.bulk from the
+// shared-memory row instead of one STG per cell (SASS: UBLKCP).  `bytes` is a multiple of 16, both addresses are
+// 16-byte aligned.  The issuing thread fences the generic-proxy writes of the row (ordered before by a barrier)
+// into the async proxy first; dev_bulk_wait_read() returns once the engine no longer reads shared memory.
+__device__ __forceinline__ void dev_bulk_store_row(void *gdst, const void *ssrc, unsigned bytes)
+{
+    const unsigned saddr = (unsigned)__cvta_generic_to_shared(ssrc);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(saddr), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void dev_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void dev_bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }

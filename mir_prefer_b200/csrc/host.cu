@@ -98,6 +98,9 @@ struct Lane {
     DBuf units, raw, loci, codes, F, C, M, Mp, ring, fillflags, tbcount, tbbase, listoff, startlist, scan_in, scan_out, scan_tmp;
     DBuf slots, tblen, tbstart, tblocus, tbflag, tbenergy, stackscr, fail, ssoff, hitidx;
     DBuf o_hits, o_arena, bounds, totals;
+    DBuf c_counts, c_soff, c_structs, c_nq, c_sbytes, c_voff, c_aoff, c_lsb, c_verd, c_vmat, c_arena, c_sout;   // fused stage 1 + 3
+    HBuf hc_structs, hc_arena, hc_verd, hc_vmat, hc_voff, hc_lsb;
+    uint64_t c_ns = 0, c_nv = 0, c_nb = 0;
     HBuf h_raw, h_loci, h_units, h_listoff, h_small, h_out, h_hits, h_arena;
     cudaEvent_t ev[12] = {};   // 0 h2d begin, 1 kernels begin, 2 fill begin, 3 fill end, 4 f3 end, 5 pack end, 6 d2h end, 7 done, 10/11 side fork/join
     // chunk in flight
@@ -121,9 +124,11 @@ struct Lane {
     {
         DBuf *all[] = {&units, &raw, &loci, &codes, &F, &C, &M, &Mp, &ring, &fillflags, &tbcount, &tbbase, &listoff, &startlist, &scan_in,
                        &scan_out, &scan_tmp, &slots, &tblen, &tbstart, &tblocus, &tbflag, &tbenergy, &stackscr, &fail,
-                       &ssoff, &hitidx, &o_hits, &o_arena, &bounds, &totals};
+                       &ssoff, &hitidx, &o_hits, &o_arena, &bounds, &totals, &c_counts, &c_soff, &c_structs, &c_nq, &c_sbytes,
+                       &c_voff, &c_aoff, &c_lsb, &c_verd, &c_vmat, &c_arena, &c_sout};
         for (DBuf *b : all) b->release();
-        HBuf *hall[] = {&h_raw, &h_loci, &h_units, &h_listoff, &h_small, &h_out, &h_hits, &h_arena};
+        HBuf *hall[] = {&h_raw, &h_loci, &h_units, &h_listoff, &h_small, &h_out, &h_hits, &h_arena, &hc_structs, &hc_arena, &hc_verd,
+                        &hc_vmat, &hc_voff, &hc_lsb};
         for (HBuf *b : hall) b->release();
         for (auto &e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
         if (s_lo) cudaStreamDestroy(s_lo);
@@ -140,10 +145,12 @@ struct Device {
     Lane lane[2];
     cudaEvent_t ev_first = nullptr, ev_last = nullptr;
     DBuf duplex_arena, duplex_q, duplex_v;   // mirfold_duplex scratch
+    DBuf cand_regions, cand_matures, cand_moff;   // the call's records (mirfold_fold_candidates)
     void release()
     {
         lane[0].release(); lane[1].release();
         duplex_arena.release(); duplex_q.release(); duplex_v.release();
+        cand_regions.release(); cand_matures.release(); cand_moff.release();
         if (ev_first) cudaEventDestroy(ev_first);
         if (ev_last) cudaEventDestroy(ev_last);
         ev_first = ev_last = nullptr;
@@ -207,7 +214,24 @@ struct SharedOut {
     }
 };
 
-enum { SINK_NONE = 0, SINK_SHARED = 1, SINK_STREAM = 2 };
+enum { SINK_NONE = 0, SINK_SHARED = 1, SINK_STREAM = 2, SINK_CAND = 3 };
+
+// fused stage 1 + 3: what the chunks of all devices append to (small: a few percent of the hit text)
+struct CandCollector {
+    std::mutex mu;
+    std::vector<mirfold_structure> structs;
+    std::vector<char> arena;
+    std::vector<mirfold_duplex_verdict> verdicts;
+    std::vector<uint32_t> verdict_mature, struct_count, verdict_count;
+    std::vector<uint64_t> struct_begin, verdict_begin;
+};
+struct CandArgs {
+    const mirfold_region *regions = nullptr;
+    const mirfold_mature *matures = nullptr;
+    const uint64_t *mature_off = nullptr;
+    uint32_t nseq = 0;
+    int minlen = 55, minloop = 3, min_mature = 18, max_mature = 24;
+};
 
 struct Job {   // one fold call; shared read-only by the device threads (sinks are synchronised)
     const char *seqs = nullptr;
@@ -221,6 +245,8 @@ struct Job {   // one fold call; shared read-only by the device threads (sinks a
     void *user = nullptr;
     std::mutex *cb_mu = nullptr;
     std::atomic<int> *cb_abort = nullptr;
+    const CandArgs *cand = nullptr;
+    CandCollector *collect = nullptr;
 };
 
 struct DevOut {
@@ -447,6 +473,17 @@ struct DevicePipeline {
             }
         }
         out.st.cells = total_cells;
+        if (J.sink == SINK_CAND) {
+            const CandArgs &c = *J.cand;
+            const uint64_t nm = c.mature_off[c.nseq];
+            CK(D.cand_regions.ensure(sizeof(mirfold_region) * (size_t)c.nseq + 16));
+            CK(D.cand_matures.ensure(sizeof(mirfold_mature) * (size_t)nm + 16));
+            CK(D.cand_moff.ensure(8 * ((size_t)c.nseq + 1)));
+            CK(cudaMemcpy(D.cand_regions.p, c.regions, sizeof(mirfold_region) * (size_t)c.nseq, cudaMemcpyHostToDevice));
+            if (nm) CK(cudaMemcpy(D.cand_matures.p, c.matures, sizeof(mirfold_mature) * (size_t)nm, cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(D.cand_moff.p, c.mature_off, 8 * ((size_t)c.nseq + 1), cudaMemcpyHostToDevice));
+            out.st.h2d_bytes += sizeof(mirfold_region) * (uint64_t)c.nseq + sizeof(mirfold_mature) * nm + 8 * ((uint64_t)c.nseq + 1);
+        }
         plan_chunks(total_cells);
         out.st.n_chunks = (int32_t)chunks.size();
         ht.mark("plan chunks");
@@ -547,7 +584,7 @@ struct DevicePipeline {
         CK(Ln.F.ensure(P.seq_acc * 4));
         CK(Ln.C.ensure(P.band_acc * 4));
         CK(Ln.M.ensure(P.band_acc * 4));
-        if (!J.force_wide) CK(Ln.Mp.ensure(P.band_acc * 4));
+        if (!J.force_wide) CK(Ln.Mp.ensure(P.band_acc * 4 + 4096));   // fML16 row pairs: NS (two copies) or NS/2 words per diagonal, by bucket
         CK(Ln.ring.ensure(P.ring_acc * 4));
         CK(Ln.tbcount.ensure((size_t)nl * 4));
         CK(Ln.tbbase.ensure((size_t)(nl + 1) * 8));
@@ -698,9 +735,13 @@ struct DevicePipeline {
         CK(launch_pack(tb, Ln.ssoff.as<unsigned long long>(), Ln.hitidx.as<unsigned long long>(), Ln.o_arena.as<char>(),
                        Ln.o_hits.as<mirfold_hit>(), Ln.arena_base, hi));
         out.st.kernel_launches += 1;
+        if (J.sink == SINK_CAND) { if (!back_candidates(Ln, last_chunk)) return false; }
+        else {
         CK(cudaEventRecord(Ln.ev[5], hi));
         if (last_chunk) CK(cudaEventRecord(D.ev_last, hi));
-        if (J.sink != SINK_NONE) {
+        }
+        if (J.sink == SINK_CAND) {
+        } else if (J.sink != SINK_NONE) {
             if (tb.ntb) {
                 k_gather_bounds<<<(nl + 1 + 255) / 256, 256, 0, hi>>>(tb.tb_base, Ln.hitidx.as<unsigned long long>(), tb.loci, tb.F,
                                                                       Ln.bounds.as<unsigned long long>(), Ln.totals.as<int>(), nl);
@@ -728,6 +769,93 @@ struct DevicePipeline {
         return true;
     }
 
+    // ---- fused stages 1 + 3 on the chunk's packed hits (still in HBM): classify, duplex verdicts, compact download
+    bool back_candidates(Lane &Ln, bool last_chunk)
+    {
+        cudaStream_t hi = Ln.s_hi;
+        TraceBuffers &tb = Ln.tb;
+        const Prep &P = Ln.prep;
+        const int nl = P.nl;
+        const uint64_t nhits = Ln.nhits;
+        const CandArgs &ca = *J.cand;
+        unsigned long long *hs = Ln.h_small.as<unsigned long long>();
+        k_gather_bounds<<<(nl + 1 + 255) / 256, 256, 0, hi>>>(tb.tb_base, Ln.hitidx.as<unsigned long long>(), tb.loci, tb.F,
+                                                              Ln.bounds.as<unsigned long long>(), Ln.totals.as<int>(), nl);
+        CK(cudaGetLastError());
+        CK(Ln.c_counts.ensure((nhits + 2) * 8)); CK(Ln.c_soff.ensure((nhits + 2) * 8));
+        CK(Ln.c_lsb.ensure((size_t)(nl + 1) * 8));
+        CandLaunch c{};
+        c.loci = tb.loci; c.nloci = nl; c.hits = Ln.o_hits.as<mirfold_hit>(); c.nhits = nhits;
+        c.arena = Ln.o_arena.as<char>(); c.arena_base = Ln.arena_base; c.bounds = Ln.bounds.as<unsigned long long>();
+        c.regions = D.cand_regions.as<mirfold_region>(); c.matures = D.cand_matures.as<mirfold_mature>();
+        c.mature_off = D.cand_moff.as<unsigned long long>();
+        c.minlen = ca.minlen; c.minloop = ca.minloop; c.min_mature = ca.min_mature; c.max_mature = ca.max_mature;
+        c.counts = Ln.c_counts.as<unsigned long long>(); c.soff = Ln.c_soff.as<unsigned long long>();
+        c.locus_sbegin = Ln.c_lsb.as<unsigned long long>();
+        c.fail_flag = Ln.fail.as<int>();
+        CK(launch_cand_classify(c, 0, hi));
+        CK(exclusive_scan(Ln, c.counts, Ln.c_soff.as<unsigned long long>(), (size_t)nhits + 1, hi));
+        CK(cudaMemcpyAsync(&hs[4], Ln.c_soff.as<unsigned long long>() + nhits, 8, cudaMemcpyDeviceToHost, hi));
+        CK(cudaMemcpyAsync(&hs[3], Ln.fail.p, 4, cudaMemcpyDeviceToHost, hi));
+        CK(cudaStreamSynchronize(hi));
+        if (*(int *)&hs[3]) { out.err = MIRFOLD_ERR_ARG; out.errmsg = "a hit on which the reference's classifier raises (no pair / unbalanced)"; return false; }
+        const uint64_t ns = Ln.c_ns = hs[4];
+        CK(Ln.c_structs.ensure(ns * sizeof(mirfold_structure) + 16)); CK(Ln.c_sout.ensure(ns * sizeof(mirfold_structure) + 16));
+        CK(Ln.c_nq.ensure((ns + 2) * 8)); CK(Ln.c_sbytes.ensure((ns + 2) * 8));
+        CK(Ln.c_voff.ensure((ns + 2) * 8)); CK(Ln.c_aoff.ensure((ns + 2) * 8));
+        CK(cudaMemsetAsync(Ln.c_nq.p, 0, (ns + 1) * 8, hi)); CK(cudaMemsetAsync(Ln.c_sbytes.p, 0, (ns + 1) * 8, hi));
+        c.structs = Ln.c_structs.as<mirfold_structure>(); c.nstructs = ns;
+        c.nq = Ln.c_nq.as<unsigned long long>(); c.sbytes = Ln.c_sbytes.as<unsigned long long>();
+        CK(launch_cand_classify(c, 1, hi));
+        CK(exclusive_scan(Ln, c.nq, Ln.c_voff.as<unsigned long long>(), (size_t)ns + 1, hi));
+        CK(exclusive_scan(Ln, c.sbytes, Ln.c_aoff.as<unsigned long long>(), (size_t)ns + 1, hi));
+        CK(cudaMemcpyAsync(&hs[5], Ln.c_voff.as<unsigned long long>() + ns, 8, cudaMemcpyDeviceToHost, hi));
+        CK(cudaMemcpyAsync(&hs[6], Ln.c_aoff.as<unsigned long long>() + ns, 8, cudaMemcpyDeviceToHost, hi));
+        CK(cudaStreamSynchronize(hi));
+        const uint64_t nv = Ln.c_nv = hs[5], nb = Ln.c_nb = hs[6];
+        CK(Ln.c_verd.ensure(nv * sizeof(mirfold_duplex_verdict) + 16)); CK(Ln.c_vmat.ensure(nv * 4 + 16)); CK(Ln.c_arena.ensure(nb + 16));
+        c.voff = Ln.c_voff.as<unsigned long long>(); c.aoff = Ln.c_aoff.as<unsigned long long>();
+        c.verdicts = Ln.c_verd.as<mirfold_duplex_verdict>(); c.verdict_mature = Ln.c_vmat.as<unsigned int>();
+        c.out_arena = Ln.c_arena.as<char>(); c.out_base = 0; c.structs_out = Ln.c_sout.as<mirfold_structure>();
+        CK(launch_cand_finish(c, P.max_Ls + 4, hi));
+        out.st.kernel_launches += 11;   // gather, 2 x classify, locus bounds, 3 x cub scan (2 kernels each), duplex, strings
+        CK(cudaEventRecord(Ln.ev[5], hi));
+        if (last_chunk) CK(cudaEventRecord(D.ev_last, hi));
+        CK(Ln.hc_structs.ensure(ns * sizeof(mirfold_structure) + 16)); CK(Ln.hc_arena.ensure(nb + 16));
+        CK(Ln.hc_verd.ensure(nv * sizeof(mirfold_duplex_verdict) + 16)); CK(Ln.hc_vmat.ensure(nv * 4 + 16));
+        CK(Ln.hc_voff.ensure((ns + 1) * 8)); CK(Ln.hc_lsb.ensure((size_t)(nl + 1) * 8));
+        if (ns) CK(cudaMemcpyAsync(Ln.hc_structs.p, Ln.c_sout.p, ns * sizeof(mirfold_structure), cudaMemcpyDeviceToHost, hi));
+        if (nb) CK(cudaMemcpyAsync(Ln.hc_arena.p, Ln.c_arena.p, nb, cudaMemcpyDeviceToHost, hi));
+        if (nv) CK(cudaMemcpyAsync(Ln.hc_verd.p, Ln.c_verd.p, nv * sizeof(mirfold_duplex_verdict), cudaMemcpyDeviceToHost, hi));
+        if (nv) CK(cudaMemcpyAsync(Ln.hc_vmat.p, Ln.c_vmat.p, nv * 4, cudaMemcpyDeviceToHost, hi));
+        CK(cudaMemcpyAsync(Ln.hc_voff.p, Ln.c_voff.p, (ns + 1) * 8, cudaMemcpyDeviceToHost, hi));
+        CK(cudaMemcpyAsync(Ln.hc_lsb.p, Ln.c_lsb.p, (size_t)(nl + 1) * 8, cudaMemcpyDeviceToHost, hi));
+        out.st.d2h_bytes += ns * sizeof(mirfold_structure) + nb + nv * (sizeof(mirfold_duplex_verdict) + 4) + (ns + 1) * 8 + (uint64_t)(nl + 1) * 8 + 64;
+        return true;
+    }
+
+    void retire_candidates(Lane &Ln)
+    {
+        const Prep &P = Ln.prep;
+        const int nl = P.nl;
+        CandCollector &C = *J.collect;
+        const uint64_t ns = Ln.c_ns, nv = Ln.c_nv, nb = Ln.c_nb;
+        const unsigned long long *lsb = Ln.hc_lsb.as<unsigned long long>(), *voff = Ln.hc_voff.as<unsigned long long>();
+        std::lock_guard<std::mutex> lk(C.mu);
+        const uint64_t bs = C.structs.size(), bv = C.verdicts.size(), ba = C.arena.size();
+        C.structs.insert(C.structs.end(), Ln.hc_structs.as<mirfold_structure>(), Ln.hc_structs.as<mirfold_structure>() + ns);
+        for (uint64_t k = bs; k < bs + ns; k++) C.structs[k].ss_off += ba;
+        C.arena.insert(C.arena.end(), Ln.hc_arena.as<char>(), Ln.hc_arena.as<char>() + nb);
+        C.verdicts.insert(C.verdicts.end(), Ln.hc_verd.as<mirfold_duplex_verdict>(), Ln.hc_verd.as<mirfold_duplex_verdict>() + nv);
+        C.verdict_mature.insert(C.verdict_mature.end(), Ln.hc_vmat.as<uint32_t>(), Ln.hc_vmat.as<uint32_t>() + nv);
+        for (uint64_t k = 0; k < ns; k++) { C.verdict_begin.push_back(bv + voff[k]); C.verdict_count.push_back((uint32_t)(voff[k + 1] - voff[k])); }
+        for (int k = 0; k < nl; k++) {
+            const uint32_t r = loci[P.cb + k].rec;
+            C.struct_begin[r] = bs + lsb[k];
+            C.struct_count[r] = (uint32_t)(lsb[k + 1] - lsb[k]);
+        }
+    }
+
     // ---- retire: wait for the lane's download, publish the chunk's per-record tables, collect stage times
     bool retire(Lane &Ln)
     {
@@ -743,6 +871,7 @@ struct DevicePipeline {
         cudaEventElapsedTime(&ms, Ln.ev[4], Ln.ev[5]); out.st.ms_trace += ms;
         cudaEventElapsedTime(&ms, Ln.ev[5], Ln.ev[6]); out.st.ms_d2h += ms;
         if (J.sink == SINK_NONE) return true;
+        if (J.sink == SINK_CAND) { retire_candidates(Ln); return true; }
         const unsigned long long *h_bounds = Ln.h_out.as<unsigned long long>();
         const int *h_total = (const int *)(h_bounds + nl + 1);
         if (J.sink == SINK_SHARED) {
@@ -852,6 +981,9 @@ struct FoldArgs {
     const uint64_t *raw_off = nullptr;
     const std::vector<std::vector<uint32_t>> *shard = nullptr;
     int n_devices = 0;   // 0 = all devices of the context
+    const CandArgs *cand = nullptr;      // SINK_CAND
+    CandCollector *collect = nullptr;
+    uint64_t *nhits_out = nullptr;
 };
 
 int fold_engine(mirfold_ctx *ctx, const FoldArgs &A, mirfold_result **out, mirfold_stats *stats_out)
@@ -882,11 +1014,12 @@ int fold_engine(mirfold_ctx *ctx, const FoldArgs &A, mirfold_result **out, mirfo
     std::mutex cb_mu;
     std::atomic<int> cb_abort{0};
     J.fn = A.fn; J.user = A.user; J.cb_mu = &cb_mu; J.cb_abort = &cb_abort;
+    J.cand = A.cand; J.collect = A.collect;
 
     std::unique_ptr<ResultOwner> R;
     SharedOut S;
     const uint64_t nt_total = nseq ? A.seq_off[nseq] - A.seq_off[0] : 0;
-    if (A.sink != SINK_STREAM) {
+    if (A.sink != SINK_STREAM && A.sink != SINK_CAND) {
         R.reset(new ResultOwner());
         R->ctx = ctx;
         R->hit_begin.assign((size_t)nseq + 1, 0);
@@ -938,6 +1071,12 @@ int fold_engine(mirfold_ctx *ctx, const FoldArgs &A, mirfold_result **out, mirfo
     for (int g = 0; g < G; g++) { add_stats(st, parts[g].st); nhits += parts[g].nhits; abytes += parts[g].arena_bytes; }
     st.n_devices = G;
 
+    if (A.sink == SINK_CAND) {
+        st.ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        if (stats_out) *stats_out = st;
+        if (A.nhits_out) *A.nhits_out = nhits;
+        return MIRFOLD_OK;
+    }
     if (A.sink == SINK_STREAM) {
         // records without a DP band (shorter than 5 nt) were never part of a device chunk
         std::vector<uint32_t> rec;
@@ -1199,6 +1338,57 @@ void mirfold_batch_free(mirfold_batch *B)
     delete B;
 }
 
+namespace {
+struct CandOwner {
+    mirfold_candidates pub;
+    CandCollector c;
+};
+}  // namespace
+
+int mirfold_fold_candidates(mirfold_ctx *ctx, const char *seqs, const uint64_t *seq_off, uint32_t nseq, int span_L, uint32_t flags,
+                            const mirfold_region *regions, const mirfold_mature *matures, const uint64_t *mature_off, int minlen,
+                            int minloop, int min_mature_len, int max_mature_len, mirfold_candidates **out)
+{
+    if (!ctx || !out || !seq_off || (!regions && nseq) || !mature_off || (!matures && mature_off[nseq])) return MIRFOLD_ERR_ARG;
+    *out = nullptr;
+    for (uint32_t r = 0; r < nseq; r++) if (mature_off[r + 1] < mature_off[r]) { ctx->last_error = "mature_off is not non-decreasing"; return MIRFOLD_ERR_ARG; }
+    std::unique_ptr<CandOwner> O(new CandOwner());
+    O->c.struct_begin.assign((size_t)nseq + 1, 0);
+    O->c.struct_count.assign((size_t)nseq + 1, 0);
+    CandArgs ca;
+    ca.regions = regions; ca.matures = matures; ca.mature_off = mature_off; ca.nseq = nseq;
+    ca.minlen = minlen; ca.minloop = minloop; ca.min_mature = min_mature_len; ca.max_mature = max_mature_len;
+    FoldArgs A;
+    A.seqs = seqs; A.seq_off = seq_off; A.nseq = nseq; A.span_L = span_L; A.flags = flags; A.sink = SINK_CAND;
+    A.cand = &ca; A.collect = &O->c;
+    uint64_t nhits = 0;
+    A.nhits_out = &nhits;
+    mirfold_stats st{};
+    const int rc = fold_engine(ctx, A, nullptr, &st);
+    if (rc != MIRFOLD_OK) return rc;
+    CandCollector &c = O->c;
+    mirfold_candidates &p = O->pub;
+    p = mirfold_candidates{};
+    p.nseq = nseq;
+    p.nstructs = c.structs.size();
+    p.struct_begin = c.struct_begin.data(); p.struct_count = c.struct_count.data();
+    p.structs = c.structs.data();
+    c.arena.push_back(0);
+    p.ss_arena = c.arena.data(); p.ss_bytes = c.arena.size() - 1;
+    p.nverdicts = c.verdicts.size();
+    p.verdict_begin = c.verdict_begin.data(); p.verdict_count = c.verdict_count.data();
+    p.verdicts = c.verdicts.data(); p.verdict_mature = c.verdict_mature.data();
+    p.nhits = nhits;
+    p.stats = st;
+    *out = &O.release()->pub;
+    return MIRFOLD_OK;
+}
+
+void mirfold_free_candidates(mirfold_candidates *c)
+{
+    if (c) delete reinterpret_cast<CandOwner *>(c);
+}
+
 int mirfold_plan_shards(const uint64_t *seq_off, uint32_t nseq, int span_L, int n_shards, uint32_t *shard_of, uint64_t *shard_cells)
 {
     if (!seq_off || n_shards < 1 || span_L < 5) return MIRFOLD_ERR_ARG;
@@ -1252,7 +1442,7 @@ int mirfold_debug_matrices(mirfold_ctx *ctx, const char *seq, uint32_t n, int sp
     const unsigned long long ring_elems = build_fill_units(&d, 1, units, bucket_first, max_n);
     const int nu = (int)units.size();
     CK(Ln.raw.ensure(n)); CK(Ln.loci.ensure(sizeof d)); CK(Ln.codes.ensure(n + 3)); CK(Ln.F.ensure((n + 3) * 4));
-    CK(Ln.C.ensure(cells * 4)); CK(Ln.M.ensure(cells * 4)); CK(Ln.Mp.ensure(cells * 4));
+    CK(Ln.C.ensure(cells * 4)); CK(Ln.M.ensure(cells * 4)); CK(Ln.Mp.ensure(cells * 4 + 4096));
     CK(Ln.ring.ensure((size_t)ring_elems * 4));
     CK(Ln.units.ensure(sizeof(LocusDesc) * (size_t)nu + 64));
     CK(cudaMemcpyAsync(Ln.raw.p, seq, n, cudaMemcpyHostToDevice, st));

@@ -123,12 +123,12 @@ struct FillLaunch {
     int max_n;
     const unsigned char *codes;
     int *C, *M, *ring;
-    unsigned int *Mp;     // narrow kernel: fML as 16-bit row pairs (same layout as M)
+    unsigned int *Mp;     // narrow kernel: fML as 16-bit row pairs (locus at band_off; layout by bucket, see dev_store_fml16)
     const DevParams *P;
     int bucket_first[5];  // loci sorted by descending n: [generic | <=608 | <=352 | <=160 | end)
     int *flags;           // per locus: 1 = the 16-bit kernel left its range, redo with the 32-bit kernel
     int force_wide;       // skip the 16-bit kernel (MIRFOLD_FLAG_WIDE)
-    int opts;             // experiment switches (env MIRFOLD_OPTS): bit 0 = no L1 prefetch in the DML strips, bit 1 = 32-bit DML strips in the narrow kernel
+    int opts;             // experiment switches (env MIRFOLD_OPTS): bit 0 = no L1 prefetch in the 32-bit DML strips, bit 1 = 32-bit DML strips in the narrow kernels
 };
 cudaError_t launch_prepare(const char *raw, const LocusDesc *loci, int nloci, unsigned long long total_codes,
                            unsigned char *codes, int *F, cudaStream_t st);
@@ -169,6 +169,43 @@ cudaError_t launch_emit(const TraceBuffers &b, cudaStream_t st);
 struct mirfold_hit;
 cudaError_t launch_pack(const TraceBuffers &b, const unsigned long long *ss_off, const unsigned long long *hit_idx,
                         char *arena, mirfold_hit *out_hits, unsigned long long arena_base, cudaStream_t st);
+// fused stage 1 + 3 over a chunk's packed hits (candidates.cu)
+struct mirfold_structure;
+struct mirfold_mature;
+struct mirfold_region;
+struct mirfold_duplex_verdict;
+struct CandLaunch {
+    // the chunk as k_pack left it
+    const LocusDesc *loci;
+    int nloci;
+    const mirfold_hit *hits;               // ss_off includes arena_base
+    unsigned long long nhits;
+    const char *arena;
+    unsigned long long arena_base;
+    const unsigned long long *bounds;      // nloci+1: first hit of every locus
+    // the call's records
+    const mirfold_region *regions;         // by record
+    const mirfold_mature *matures;
+    const unsigned long long *mature_off;  // by record, nseq+1
+    int minlen, minloop, min_mature, max_mature;
+    // classification
+    unsigned long long *counts;            // nhits+1 (scan input)
+    const unsigned long long *soff;        // nhits+1 (exclusive scan of counts)
+    mirfold_structure *structs;            // chunk-relative ss_off
+    unsigned long long nstructs;
+    unsigned long long *nq, *sbytes;       // per structure (+1): verdicts / string bytes (scan inputs)
+    const unsigned long long *voff, *aoff; // their exclusive scans
+    unsigned long long *locus_sbegin;      // nloci+1: first structure of every locus
+    // outputs
+    mirfold_duplex_verdict *verdicts;
+    unsigned int *verdict_mature;
+    char *out_arena;
+    unsigned long long out_base;           // added to the compact-arena offsets
+    mirfold_structure *structs_out;
+    int *fail_flag;
+};
+cudaError_t launch_cand_classify(const CandLaunch &a, int pass, cudaStream_t st);
+cudaError_t launch_cand_finish(const CandLaunch &a, int max_len, cudaStream_t st);
 cudaError_t run_int_peak(cudaStream_t st, int sm_count, double *addmin, double *dpx, double *s16x2);
 struct mirfold_duplex_query;
 struct mirfold_duplex_verdict;

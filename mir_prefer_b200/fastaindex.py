@@ -7,8 +7,10 @@ wall-clock bottleneck.  `FastaIndex.fetch_region()` returns the same string from
 no GPU involved.  Semantics follow samtools' region rules: coordinates are 1-based and inclusive,
 a region end beyond the contig is clipped, a start beyond the contig (or an unknown contig) gives
 an empty sequence, letters are returned exactly as stored (case and IUPAC codes preserved), line
-wrapping of the FASTA file is invisible.  `samtools` itself cannot run in the build container
-(SURVEY 8c), so these rules are pinned by tests on synthetic FASTA files, not by the binary.
+wrapping of the FASTA file is invisible, a region with a dangling dash ("seqid:3-") is empty (the
+end parses as 0).  Pinned to the reference's own bundled samtools 0.1.18: tests/golden/faidx.json holds
+its stdout and .fai for seeded FASTA files (tests/golden/make_golden_faidx.py; the binary only starts
+against the no-op curses stub oracle/ncurses_stub.c because the image lacks libncurses.so.5).
 """
 import os
 
@@ -62,7 +64,7 @@ class FastaIndex:
         a, dash, b = span.replace(",", "").partition("-")
         try:
             start = int(a)
-            end = int(b) if dash and b else 1 << 62
+            end = (int(b) if b else 0) if dash else 1 << 62      # "seqid:3-": samtools 0.1.18 reads the missing end as 0
         except ValueError:
             return self.fetch(region, 1, 1 << 62)
         return self.fetch(seqid, start, end)

@@ -203,6 +203,69 @@ class FoldChunk:
         return out
 
 
+MATURE_DTYPE = np.dtype([("start", "<i4"), ("end", "<i4"), ("strand", "<i4"), ("depth", "<i4")])
+REGION_DTYPE = np.dtype([("start", "<i4"), ("end", "<i4")])
+
+
+class Candidates:
+    """Result of MirFold.fold_candidates(): per record the candidate structures the predict stage consumes and, for every
+    (structure, size-admissible mature) pair, the get_maturestar_info() verdict -- computed on the device right after
+    traceback (mirfold_fold_candidates).  Everything is copied out of the library's buffers at construction."""
+
+    def __init__(self, lib, ptr, matures, mature_off):
+        c = ptr.contents
+        self.nseq, self.nstructs, self.nverdicts, self.nhits = int(c.nseq), int(c.nstructs), int(c.nverdicts), int(c.nhits)
+        self.stats = c.stats.as_dict()
+        ns, nv, n = self.nstructs, self.nverdicts, self.nseq
+        self.struct_begin = np.ctypeslib.as_array(c.struct_begin, shape=(n,)).copy() if n else np.zeros(0, np.uint64)
+        self.struct_count = np.ctypeslib.as_array(c.struct_count, shape=(n,)).copy() if n else np.zeros(0, np.uint32)
+        self.structs = (np.ctypeslib.as_array(C.cast(c.structs, C.POINTER(C.c_uint8)), shape=(ns * C.sizeof(_lib.Structure),))
+                        .view(STRUCT_DTYPE).copy() if ns else np.zeros(0, STRUCT_DTYPE))
+        self.arena = C.string_at(c.ss_arena, int(c.ss_bytes)) if ns else b""
+        self.verdict_begin = np.ctypeslib.as_array(c.verdict_begin, shape=(ns,)).copy() if ns else np.zeros(0, np.uint64)
+        self.verdict_count = np.ctypeslib.as_array(c.verdict_count, shape=(ns,)).copy() if ns else np.zeros(0, np.uint32)
+        self.verdicts = (np.ctypeslib.as_array(C.cast(c.verdicts, C.POINTER(C.c_uint8)), shape=(nv * C.sizeof(_lib.DuplexVerdict),))
+                         .view(DUPLEX_VERDICT_DTYPE).copy() if nv else np.zeros(0, DUPLEX_VERDICT_DTYPE))
+        self.verdict_mature = np.ctypeslib.as_array(c.verdict_mature, shape=(nv,)).copy() if nv else np.zeros(0, np.uint32)
+        self._matures, self._mature_off = matures, mature_off
+        self._names = {k: lib.mirfold_duplex_fail_name(k).decode() for k in list(range(12)) + [100]}
+        lib.mirfold_free_candidates(ptr)
+
+    def _ss(self, k):
+        o, n = int(self.structs["ss_off"][k]), int(self.structs["len"][k])
+        return self.arena[o:o + n].decode("ascii")
+
+    def structures(self, r):
+        """[(norm_energy, fold_start, ss, sstype)] of record r: get_structures_next_extendregion()'s third tuple field."""
+        b = int(self.struct_begin[r])
+        st = self.structs
+        return [(float(st["norm_energy"][k]), int(st["fold_start"][k]), self._ss(k), int(st["sstype"][k]))
+                for k in range(b, b + int(self.struct_count[r]))]
+
+    def verdicts_of(self, r):
+        """[(structure index within the record, mature tuple (start, end, strand, depth), verdict)] with the verdict in
+        get_maturestar_info()'s own format (9-tuple or FAIL_* string; DUPLEX_EXCEPTION where the reference raises)."""
+        out = []
+        b = int(self.struct_begin[r])
+        mb = int(self._mature_off[r])
+        for k in range(b, b + int(self.struct_count[r])):
+            ss = self._ss(k)
+            vb = int(self.verdict_begin[k])
+            for v in range(vb, vb + int(self.verdict_count[k])):
+                m = self._matures[mb + int(self.verdict_mature[v])]
+                out.append((k - b, (int(m["start"]), int(m["end"]), chr(int(m["strand"])), int(m["depth"])), self._verdict(ss, v)))
+        return out
+
+    def _verdict(self, ss, v):
+        V = self.verdicts[v]
+        c = int(V["code"])
+        if c != 0:
+            return self._names[c]
+        return (int(V["star_start"]), int(V["star_end"]), int(V["fold_start"]), int(V["fold_end"]),
+                ss[int(V["star_ss_begin"]):int(V["star_ss_end"])], bool(V["prime5"]),
+                ss[int(V["mature_ss_begin"]):int(V["mature_ss_end"])], int(V["total_dots"]), int(V["total_bps"]))
+
+
 class Batch:
     """Records sharded over the context's devices with their sequences resident in HBM (mirfold_batch_*)."""
 
@@ -321,6 +384,35 @@ class MirFold:
         if rc != 0:
             self._raise(rc)
         return st.as_dict()
+
+    def fold_candidates(self, buf, off, span, regions, matures, mature_off, minlen=55, minloop=3, min_mature_len=18,
+                        max_mature_len=24, flags=0):
+        """mirfold_fold_candidates(): fold + stage 1 (candidate structures) + stage 3 (duplex verdicts for every candidate
+        structure x size-admissible mature of its record), all on the device; only the candidates are downloaded.
+        regions: (nseq, 2) ints [start, end); matures: array of MATURE_DTYPE (or (start, end, strand_char, depth) tuples);
+        mature_off: nseq+1 offsets into matures."""
+        buf = np.ascontiguousarray(buf, np.uint8)
+        off = np.ascontiguousarray(off, np.uint64)
+        nseq = len(off) - 1
+        reg = np.zeros(nseq, REGION_DTYPE)
+        if nseq:
+            ra = np.asarray(regions, np.int64).reshape(nseq, 2)
+            reg["start"], reg["end"] = ra[:, 0], ra[:, 1]
+        if isinstance(matures, np.ndarray) and matures.dtype == MATURE_DTYPE:
+            mat = np.ascontiguousarray(matures)
+        else:
+            mat = np.zeros(len(matures), MATURE_DTYPE)
+            for k, m in enumerate(matures):
+                mat[k] = (m[0], m[1], ord(m[2]) if isinstance(m[2], str) else int(m[2]), m[3] if len(m) > 3 else 0)
+        moff = np.ascontiguousarray(mature_off, np.uint64)
+        res = C.POINTER(_lib.Candidates)()
+        rc = self._lib.mirfold_fold_candidates(self._ctx, buf.ctypes.data_as(C.c_void_p), off.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                               nseq, int(span), int(flags), reg.ctypes.data_as(C.c_void_p),
+                                               mat.ctypes.data_as(C.c_void_p), moff.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                               int(minlen), int(minloop), int(min_mature_len), int(max_mature_len), C.byref(res))
+        if rc != 0:
+            self._raise(rc)
+        return Candidates(self._lib, res, mat, moff)
 
     def upload(self, buf, off, span):
         """mirfold_batch_upload(): shard the records over the context's devices and keep their sequences in HBM."""

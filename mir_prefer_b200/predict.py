@@ -49,6 +49,22 @@ class DuplexTable:
         self.n_queries = len(queries)
         self._table = dict(zip(keys, mf.duplex(queries))) if queries else {}
 
+    @classmethod
+    def from_candidates(cls, cand, records):
+        """The same table from a fused device pass (MirFold.fold_candidates): `cand` already holds the verdict of every
+        (candidate structure, size-admissible mature) pair of every record; `records` are the LocusRecords (or anything
+        with .region) the candidates were computed for, in order."""
+        self = cls.__new__(cls)
+        self._table = {}
+        for r, rec in enumerate(records):
+            rs, re_ = rec.region[0], rec.region[1]
+            structs = cand.structures(r)
+            for k, (m0, m1, strand, _depth), verdict in cand.verdicts_of(r):
+                _e, foldstart, ss, _t = structs[k]
+                self._table[(ss, m0, m1, foldstart, rs, re_, strand)] = verdict
+        self.n_queries = cand.nverdicts
+        return self
+
     def __call__(self, ss, mature, foldstart, foldend, regionstart, regionend, strand):
         v = self._table[(ss, mature[0], mature[1], foldstart, regionstart, regionend, strand)]
         if v == DUPLEX_EXCEPTION:

@@ -156,6 +156,25 @@ class RecordFold:
         self.close()
 
 
+def candidates_of_records(mf, records, span, minlen=55, minloop=3, min_mature_len=18, max_mature_len=24):
+    """Records -> (ss_records, DuplexTable) in ONE fused device pass (mirfold_fold_candidates): the fold, the candidate
+    structures of get_structures_next_extendregion (miR_PREFeR.py:1566-1589) and get_maturestar_info (:1876-1999) for every
+    (structure, mature) pair.  ss_records is what filter_next_loci consumes: (which, peak, structures) per record."""
+    import numpy as np
+    from .predict import DuplexTable
+    records = list(records)
+    seqs = [_oriented_sequence(r) for r in records]
+    buf, off = mf.pack(seqs)
+    matures, moff = [], [0]
+    for r in records:
+        matures.extend(r.matures)
+        moff.append(len(matures))
+    cand = mf.fold_candidates(buf, off, span, [[r.region[0], r.region[1]] for r in records], matures, np.array(moff, np.uint64),
+                              minlen, minloop, min_mature_len, max_mature_len)
+    ss_records = [(rec.tag, "%s-%s" % (rec.locus[0], rec.locus[1]), cand.structures(k)) for k, rec in enumerate(records)]
+    return ss_records, DuplexTable.from_candidates(cand, records), cand
+
+
 def fold_records(mf, records, span):
     """Fold LocusRecords on the device.  Identical oriented sequences (the reference writes
     duplicated records for both-strand L/R loci) are folded once; record count and

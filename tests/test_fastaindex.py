@@ -1,6 +1,11 @@
-"""in-memory `samtools faidx` replacement (host-only).  samtools cannot run in the build
-container, so the region rules are pinned on synthetic FASTA files."""
+"""in-memory `samtools faidx` replacement (host-only), pinned to the stdout of the reference's own
+bundled samtools 0.1.18 (tests/golden/faidx.json, made by tests/golden/make_golden_faidx.py) and to synthetic FASTA files."""
+import json
+import os
+
 import numpy as np
+
+from conftest import GOLDEN
 
 from mir_prefer_b200.fastaindex import FastaIndex, write_fai
 
@@ -62,3 +67,22 @@ def test_write_fai(tmp_path):
         if length:
             assert (lb, lw) == (50, 51)
             assert raw[off:off + min(lb, length)].decode() == seqs[name][:min(lb, length)]
+
+
+def test_matches_reference_samtools_stdout(tmp_path):
+    """Every query of the golden fixture: the text `samtools faidx fasta region` printed (header + 60-column lines),
+    what dump_piece keeps of it ("".join(stdout.split("\\n")[1:]), miR_PREFeR.py:1105), and the .fai index."""
+    d = json.load(open(os.path.join(GOLDEN, "faidx.json")))
+    nq = 0
+    for k, case in enumerate(d["cases"]):
+        fa = tmp_path / ("g%d.fa" % k)
+        fa.write_text(case["fasta"])
+        fx = FastaIndex(str(fa))
+        assert open(write_fai(str(fa))).read() == case["fai"]
+        for q in case["queries"]:
+            kept = "".join(q["stdout"].split("\n")[1:])
+            assert fx.fetch_region(q["region"]) == kept, q["region"]
+            if q["rc"] == 0:                       # an unknown bare contig name makes samtools 0.1.18 crash without output
+                assert fx.faidx_stdout(q["region"]) == q["stdout"], q["region"]
+            nq += 1
+    assert nq >= 90

@@ -116,6 +116,99 @@ def test_check_loci_early_exits():
         assert r[tuple(region)]["HAS_MATURE_SIZE_IN_RANGE"] == "FAILED"
 
 
+# ------------------------------------------------------------------------------------ composed end to end
+@pytest.fixture(scope="module")
+def e2e_cases():
+    d = json.load(open(os.path.join(GOLDEN, "e2e_mirna.json")))
+    for c in d["cases"]:
+        c["records"] = [R.LocusRecord(x[0], tuple(x[1]), x[2], tuple(x[3]), x[4], [tuple(p) for p in x[5]], [tuple(m) for m in x[6]], x[7])
+                        for x in c["records"]]
+    return d
+
+
+def _aln_of(records):
+    return [[[r.seqid, r.region, r.strand], r.tag, {}, list(r.matures)] for r in records]
+
+
+def test_end_to_end_mirna_list_oracle_path(e2e_cases, oracle, tmp_path):
+    """CPU: records -> FASTA -> oracle RNALfold text -> parser restatement -> consumer restatement with the duplex oracle
+    == the list the reference's own binary + parser + filter_next_loci produced (tests/golden/make_golden_e2e.py)."""
+    import duplex_oracle as DO
+
+    def maturestar(ss, mature, foldstart, foldend, rs, re_, strand):
+        return DO.maturestar(ss, mature, foldstart, rs, re_, strand)
+
+    case = e2e_cases["cases"][0]
+    fa = tmp_path / "shard.fa"
+    R.write_fasta(case["records"], str(fa))
+    out = tmp_path / "shard_rnalfoldoutput_0"
+    out.write_text(oracle.fold_text(fa.read_text(), e2e_cases["span"]))
+    ssrecs = list(S.get_structures_next_extendregion(str(out), 55, 3))
+    for key in ("11", "10", "01", "00"):
+        got = run_ours(_aln_of(case["records"]), ssrecs, key[0] == "1", key[1] == "1", maturestar)
+        assert got == case["expected"][key], key
+    assert sum(isinstance(x, list) for x in case["expected"]["11"]) >= 5
+
+
+@pytest.mark.gpu
+def test_end_to_end_mirna_list_fused_device_path(mf, e2e_cases):
+    """GPU: the same records through ONE fused device pass (fold + stage 1 + stage 3, mirfold_fold_candidates) and the host
+    consumer: identical final miRNA list and identical reasons, for every option combination."""
+    for case in e2e_cases["cases"]:
+        ssrecs, table, cand = R.candidates_of_records(mf, case["records"], e2e_cases["span"])
+        assert cand.nverdicts > 100 and cand.nstructs > 100
+        for key in ("11", "10", "01", "00"):
+            got = run_ours(_aln_of(case["records"]), ssrecs, key[0] == "1", key[1] == "1", table)
+            assert got == case["expected"][key], (case["seed"], key)
+
+
+@pytest.mark.gpu
+def test_fused_candidates_equal_separate_stages(mf):
+    """mirfold_fold_candidates == mirfold_fold + mirfold_classify + mirfold_duplex on the same records (several chunks,
+    two pipelines on one GPU), and the download is a small fraction of the hit text."""
+    import numpy as np
+    import mir_prefer_b200 as mp
+    from mir_prefer_b200.corpus import synth_loci
+    seqs = synth_loci(61, 400, "arabidopsis") + ["", "ACGT"]
+    rng = np.random.default_rng(9)
+    regions, matures, moff = [], [], [0]
+    for s in seqs:
+        rs = int(rng.integers(1, 50000))
+        regions.append([rs, rs + len(s)])
+        for _ in range(int(rng.integers(0, 4))):
+            mlen = int(rng.choice([16, 20, 21, 22, 25]))
+            strand = "+-"[int(rng.integers(2))]
+            m0 = rs + int(rng.integers(0, max(1, len(s) - mlen)))
+            matures.append((m0, m0 + mlen, strand, int(rng.integers(1, 99))))
+        moff.append(len(matures))
+    buf, off = mf.pack(seqs)
+    with mf.fold_packed(buf, off, 300) as res:
+        per_rec = res.classify(55)
+        d2h_full = res.stats["d2h_bytes"]
+    queries, keys = [], []
+    for r, structs in enumerate(per_rec):
+        for k, (_e, fs, ss, _t) in enumerate(structs):
+            for m in matures[moff[r]:moff[r + 1]]:
+                if 18 <= m[1] - m[0] <= 24:
+                    queries.append((ss, (m[0], m[1]), fs, regions[r][0], regions[r][1], m[2]))
+                    keys.append((r, k, m))
+    want = dict(zip(keys, mf.duplex(queries)))
+    os.environ["MIRFOLD_MEM_BUDGET_MB"] = "64"
+    try:
+        with mp.MirFold(devices=[0, 0]) as m2:
+            cand = m2.fold_candidates(buf, off, 300, regions, matures, np.array(moff, np.uint64))
+    finally:
+        del os.environ["MIRFOLD_MEM_BUDGET_MB"]
+    assert cand.stats["n_chunks"] >= 4
+    got = {}
+    for r in range(len(seqs)):
+        assert cand.structures(r) == per_rec[r], r
+        for k, m, v in cand.verdicts_of(r):
+            got[(r, k, m)] = v
+    assert got == want and len(want) > 300
+    assert cand.stats["d2h_bytes"] < 0.25 * d2h_full
+
+
 # ------------------------------------------------------------------------------------ GPU
 @pytest.mark.gpu
 def test_predict_consumer_with_device_duplex_table(mf, predict_cases):
