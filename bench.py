@@ -315,13 +315,18 @@ def run_ours(args, rank, world, local_rank):
     if not os.path.exists(_lib.LIB_PATH):
         raise RuntimeError("libmirfold.so missing (run python __graft_entry__.py); there is no CPU fallback")
     torch.cuda.set_device(local_rank)
+    cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.barrier()                                   # the NCCL communicator over all N ranks exists and works
+        cpu_group = dist.new_group(backend="gloo")
 
     def barrier():
-        if world > 1:
-            dist.barrier()
+        # Ranks > 0 wait on the CPU (gloo): an NCCL barrier would park a spinning kernel on every waiting GPU, and those
+        # are the GPUs rank 0's context is folding on (two processes time-slice a GPU: measured 2x slower at N = 2).
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(group=cpu_group)
 
     out = None
     if rank == 0:
@@ -368,6 +373,7 @@ def run_ours(args, rank, world, local_rank):
         # ---- per-kernel durations for the roofline: one pass with a single lane per device, so that the CUDA-event
         # brackets of the stages are disjoint (in the pipelined passes a chunk's fill shares the SMs with the previous
         # chunk's traceback)
+        batch.fold(flags=FLAG_SERIAL).close()            # the single-lane chunking sizes its buffers once
         with batch.fold(flags=FLAG_SERIAL) as r:
             serial = {k: r.stats[k] for k in ("ms_fill", "ms_f3", "ms_trace", "ms_device")}
         _, shard_cells = plan_shards(lens, SPAN, world)
@@ -452,6 +458,7 @@ def run_ours(args, rank, world, local_rank):
                                    "dp_cells_per_s": snt / dt * (float(cells) / max(nt, 1))}
         print(json.dumps(out))
     if world > 1:
+        torch.cuda.synchronize()
         dist.barrier()
         dist.destroy_process_group()
 
@@ -471,8 +478,25 @@ def drop_in_stages(mf, buf, off, lens):
     t0 = time.perf_counter()
     verdicts = mf.duplex(queries)
     t_dup = time.perf_counter() - t0
-    return {"loci": n, "classify_structures_ms": 1e3 * t_cls, "structures": nstruct, "duplex_queries_ms": 1e3 * t_dup,
-            "duplex_queries": len(queries), "duplex_pass": sum(1 for v in verdicts if not isinstance(v, str))}
+    out = {"loci": n, "classify_structures_ms": 1e3 * t_cls, "structures": nstruct, "duplex_queries_ms": 1e3 * t_dup,
+           "duplex_queries": len(queries), "duplex_pass": sum(1 for v in verdicts if not isinstance(v, str))}
+    # the same two stages fused on the device after traceback (mirfold_fold_candidates): whole call vs the plain fold
+    regions = np.stack([np.ones(n, np.int64), lens[:n].astype(np.int64) + 1], axis=1)
+    matures = np.zeros(n, [("start", "<i4"), ("end", "<i4"), ("strand", "<i4"), ("depth", "<i4")])
+    matures["start"], matures["end"], matures["strand"], matures["depth"] = 40, 61, ord("+"), 50
+    moff = np.arange(n + 1, dtype=np.uint64)
+    mf.fold_candidates(sub_buf, sub_off, SPAN, regions, matures, moff)
+    t0 = time.perf_counter()
+    cand = mf.fold_candidates(sub_buf, sub_off, SPAN, regions, matures, moff)
+    t_fused = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    with mf.fold_packed(sub_buf, sub_off, SPAN) as r:
+        d2h_plain = r.stats["d2h_bytes"]
+    t_plain = time.perf_counter() - t0
+    out["fused"] = {"fold_candidates_ms": 1e3 * t_fused, "plain_fold_ms": 1e3 * t_plain, "stage1_3_on_device_ms": 1e3 * (t_fused - t_plain),
+                    "structures": cand.nstructs, "verdicts": cand.nverdicts, "d2h_bytes": cand.stats["d2h_bytes"],
+                    "d2h_bytes_plain_fold": d2h_plain}
+    return out
 
 
 def main():

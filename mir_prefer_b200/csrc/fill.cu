@@ -591,6 +591,8 @@ __global__ void __launch_bounds__(NT, MINB) k_fill_smem(FillLaunch a)
     const int n = L.n, Ls = L.Ls, dmax = L.dmax;
     const DevParams *__restrict__ P = a.P;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    // no traceback hint from this kernel: every cell says "scan the two-loop candidates"
+    for (int k = tid; k < (dmax - 3) * (NS / 4); k += NT) ((unsigned int *)(a.Ib + L.band_off))[k] = 0x01010101u;
 
     for (int k = tid; k < NS + 8; k += NT) {
         const unsigned char b = (k < n + 3) ? a.codes[L.seq_off + k] : 0;
@@ -776,7 +778,7 @@ template <class StrideT>
 __device__ __forceinline__ int dev_cell_tail16(const DevParams *__restrict__ P, const unsigned char *sS,
                                                const unsigned char *sS1, const unsigned char *sPair,
                                                const unsigned int *sB, int RS, const int *rD, StrideT NS, int i,
-                                               int d, int t, int si1, int sj1, int K)
+                                               int d, int t, int si1, int sj1, int K, int &two_loop_min)
 {
     const int j = i + d;
     const int AUp = P->TerminalAU;
@@ -801,6 +803,7 @@ __device__ __forceinline__ int dev_cell_tail16(const DevParams *__restrict__ P, 
         else e = P->int22[((((t * 8 + r2) * 5 + si1) * 5 + sp1) * 5 + sq1) * 5 + sj1];
         if (ok && t2) best = min(best, e + c2);
     }
+    two_loop_min = best;
     best = min(best, dev_hairpin(P, sS, sS1, i, j, t));
     const int tt = dev_rtype(t);
     const int d3 = P->dangle3[tt * 5 + si1], d5 = P->dangle5[tt * 5 + sj1];
@@ -896,6 +899,7 @@ __global__ void __launch_bounds__(NT, MINB) k_fill_s16(FillLaunch a)
 
     int *Cb = a.C + L.band_off;
     int *Mb = a.M + L.band_off;
+    unsigned char *Ib = a.Ib + L.band_off;     // one byte per band cell, written for every typed cell (the only ones a traceback asks about)
     constexpr bool OC = NS <= 352;           // fML16 layout of this bucket (see dev_store_fml16)
 #ifdef MF_NO_BULK_ROWS
     constexpr bool BULK = false;
@@ -997,11 +1001,15 @@ __global__ void __launch_bounds__(NT, MINB) k_fill_s16(FillLaunch a)
                     const int my = sMy[c];
                     const int t = sPair[sS[i] * 8 + sS[j]];
                     const int si1 = sS1[i + 1], sj1 = sS1[j - 1];
-                    int best = (my < MF16_VALID) ? my + sMM[(t * 5 + si1) * 5 + sj1] : MF_INF;
-                    best = min(best, dev_cell_tail16(P, sS, sS1, sPair, sB, RS, rD, NS, i, d, t, si1, sj1, K));
+                    const int wide_loops = (my < MF16_VALID) ? my + sMM[(t * 5 + si1) * 5 + sj1] : MF_INF;
+                    int small_loops;
+                    const int best = min(wide_loops, dev_cell_tail16(P, sS, sS1, sPair, sB, RS, rD, NS, i, d, t, si1, sj1, K, small_loops));
                     const int tt = dev_rtype(t);
                     const int mm = sMM[(tt * 5 + sS1[j + 1]) * 5 + sS1[i - 1]];
                     Cb[(d - 4) * NS + i - 1] = best;
+                    // traceback hint: some two-loop (p,q) reproduces c(i,j).  Where the bit stays 0 the traceback skips its
+                    // 496-candidate scan and goes straight to the multiloop decomposition (58 % of its scan rounds end there)
+                    Ib[(d - 4) * NS + i - 1] = (unsigned char)(min(wide_loops, small_loops) == best);
                     if (best < MF16_GUARD) sFlag = 1;
                     dev_ring16_put(sG, RS, d, i - 1, max(best + mm, -32768));
                     dev_ring16_put(sB, RS, d, i - 1, max(best + (tt > 2 ? AUp : 0), -32768));
@@ -1091,6 +1099,7 @@ __global__ void __launch_bounds__(NT) k_fill_generic(FillLaunch a)
     int *Mb = a.M + L.band_off;
     int *rD = a.ring + L.ring_off;                              // [MF_RING_DML][NS]
     int *rCm = rD + (unsigned long long)MF_RING_DML * NS;       // [MF_RING_CM][NS]
+    for (long long k = tid; k < (long long)(dmax - 3) * (NS / 4); k += NT) ((unsigned int *)(a.Ib + L.band_off))[k] = 0x01010101u;   // no traceback hint
     for (int k = tid; k < MF_RING_DML * NS; k += NT) rD[k] = MF_INF;
     __syncthreads();
 

@@ -95,7 +95,7 @@ struct Lane {
     cudaStream_t s_lo = nullptr;   // uploads, encode, band fill
     cudaStream_t s_hi = nullptr;   // f3, plan, traceback, pack, downloads (high priority: gets freed SM slots first)
     cudaStream_t side = nullptr;   // small fill buckets run here, concurrently with the big one
-    DBuf units, raw, loci, codes, F, C, M, Mp, ring, fillflags, tbcount, tbbase, listoff, startlist, scan_in, scan_out, scan_tmp;
+    DBuf units, raw, loci, codes, F, C, M, Mp, Ib, ring, fillflags, tbcount, tbbase, listoff, startlist, scan_in, scan_out, scan_tmp;
     DBuf slots, tblen, tbstart, tblocus, tbflag, tbenergy, stackscr, fail, ssoff, hitidx;
     DBuf o_hits, o_arena, bounds, totals;
     DBuf c_counts, c_soff, c_structs, c_nq, c_sbytes, c_voff, c_aoff, c_lsb, c_verd, c_vmat, c_arena, c_sout;   // fused stage 1 + 3
@@ -122,7 +122,7 @@ struct Lane {
     }
     void release()
     {
-        DBuf *all[] = {&units, &raw, &loci, &codes, &F, &C, &M, &Mp, &ring, &fillflags, &tbcount, &tbbase, &listoff, &startlist, &scan_in,
+        DBuf *all[] = {&units, &raw, &loci, &codes, &F, &C, &M, &Mp, &Ib, &ring, &fillflags, &tbcount, &tbbase, &listoff, &startlist, &scan_in,
                        &scan_out, &scan_tmp, &slots, &tblen, &tbstart, &tblocus, &tbflag, &tbenergy, &stackscr, &fail,
                        &ssoff, &hitidx, &o_hits, &o_arena, &bounds, &totals, &c_counts, &c_soff, &c_structs, &c_nq, &c_sbytes,
                        &c_voff, &c_aoff, &c_lsb, &c_verd, &c_vmat, &c_arena, &c_sout};
@@ -435,7 +435,7 @@ size_t locus_bytes(int n, int L)
     LocusDesc d{};
     const unsigned long long be = shape_locus(d, n, L);
     const size_t per_tb = (size_t)((std::min(L, n) + 8) & ~3) + (size_t)(std::min(L, n) / 4 + 16) * 8 + 64;
-    return (size_t)be * 12 + (size_t)(d.tile_last + 1) * unit_ring_elems(std::min(n, d.tile_last ? MF_TILE_LEN : n), d.stride) * 4 +
+    return (size_t)be * 13 + (size_t)(d.tile_last + 1) * unit_ring_elems(std::min(n, d.tile_last ? MF_TILE_LEN : n), d.stride) * 4 +
            (size_t)(d.tile_last + 2) * sizeof(LocusDesc) + (size_t)n * 16 + (size_t)(n / 8 + 2) * per_tb + 4096;
 }
 
@@ -517,12 +517,14 @@ struct DevicePipeline {
         return true;
     }
 
-    // chunks of about equal device bytes, each within a lane's budget; when results are downloaded a shard is cut
-    // into a few more chunks than memory demands so that downloads and host work overlap the next chunk's fill
+    // chunks of about equal device bytes, each within a lane's budget.  A chunk boundary costs about 1.2 ms of device time
+    // (launch train, two host syncs, wave tails the other lane only partly fills: 25 k loci in 1 / 2 / 4 / 9 chunks = 106.0 /
+    // 108.3 / 108.0 / 111.5 ms end to end; 200 k loci in 7 / 16 / 37 chunks = 855.0 / 849.2 / 855.4) while a download runs at 55 GB/s, so a shard is only cut further than memory
+    // demands when it is long enough for the last chunk's download (the only one not overlapped) to matter
     void plan_chunks(uint64_t total_cells)
     {
         if (loci.empty()) return;
-        static const double cells_per_chunk = getenv("MIRFOLD_CHUNK_CELLS") ? atof(getenv("MIRFOLD_CHUNK_CELLS")) : 2.5e8;
+        static const double cells_per_chunk = getenv("MIRFOLD_CHUNK_CELLS") ? atof(getenv("MIRFOLD_CHUNK_CELLS")) : 6.0e8;
         std::vector<size_t> lb(loci.size());
         size_t total = 0;
         int last_n = -1; size_t last_b = 0;
@@ -584,6 +586,7 @@ struct DevicePipeline {
         CK(Ln.F.ensure(P.seq_acc * 4));
         CK(Ln.C.ensure(P.band_acc * 4));
         CK(Ln.M.ensure(P.band_acc * 4));
+        CK(Ln.Ib.ensure(P.band_acc + 256));
         if (!J.force_wide) CK(Ln.Mp.ensure(P.band_acc * 4 + 4096));   // fML16 row pairs: NS (two copies) or NS/2 words per diagonal, by bucket
         CK(Ln.ring.ensure(P.ring_acc * 4));
         CK(Ln.tbcount.ensure((size_t)nl * 4));
@@ -619,7 +622,7 @@ struct DevicePipeline {
         CK(launch_prepare(raw_dev, dl, nl, P.seq_acc, Ln.codes.as<unsigned char>(), Ln.F.as<int>(), lo));
         CK(cudaEventRecord(Ln.ev[2], lo));
         FillLaunch fa{Ln.units.as<LocusDesc>(), nu, P.max_n, Ln.codes.as<unsigned char>(), Ln.C.as<int>(), Ln.M.as<int>(), Ln.ring.as<int>(),
-                      Ln.Mp.as<unsigned int>(), D.dP, {0, 0, 0, 0, 0}, Ln.fillflags.as<int>(), J.force_wide ? 1 : 0, env_opts()};
+                      Ln.Ib.as<unsigned char>(), Ln.Mp.as<unsigned int>(), D.dP, {0, 0, 0, 0, 0}, Ln.fillflags.as<int>(), J.force_wide ? 1 : 0, env_opts()};
         for (int b = 0; b < 5; b++) fa.bucket_first[b] = P.bucket_first[b];
         static const bool no_side = getenv("MIRFOLD_NO_SIDE_STREAM") != nullptr;   // A/B runs
         CK(launch_fill(fa, lo, no_side ? nullptr : Ln.side, Ln.ev[10], Ln.ev[11]));
@@ -636,7 +639,7 @@ struct DevicePipeline {
         TraceBuffers &tb = Ln.tb;
         tb = TraceBuffers{};
         tb.loci = dl; tb.nloci = nl; tb.codes = Ln.codes.as<unsigned char>();
-        tb.C = Ln.C.as<int>(); tb.M = Ln.M.as<int>(); tb.F = Ln.F.as<int>(); tb.P = D.dP;
+        tb.C = Ln.C.as<int>(); tb.M = Ln.M.as<int>(); tb.F = Ln.F.as<int>(); tb.Ib = Ln.Ib.as<unsigned char>(); tb.P = D.dP;
         tb.tb_count = Ln.tbcount.as<int>(); tb.tb_base = Ln.tbbase.as<unsigned long long>();
         tb.list_off = Ln.listoff.as<unsigned long long>(); tb.tb_start_list = Ln.startlist.as<int>();
         tb.fail_flag = Ln.fail.as<int>();
@@ -870,6 +873,13 @@ struct DevicePipeline {
         cudaEventElapsedTime(&ms, Ln.ev[3], Ln.ev[4]); out.st.ms_f3 += ms;
         cudaEventElapsedTime(&ms, Ln.ev[4], Ln.ev[5]); out.st.ms_trace += ms;
         cudaEventElapsedTime(&ms, Ln.ev[5], Ln.ev[6]); out.st.ms_d2h += ms;
+        static const bool trace_events = getenv("MIRFOLD_TRACE_EVENTS") != nullptr;
+        if (trace_events) {   // device timeline of the chunk relative to the call's first event (ms)
+            float t[7];
+            for (int k = 0; k < 7; k++) cudaEventElapsedTime(&t[k], D.ev_first, Ln.ev[k]);
+            fprintf(stderr, "[mirfold events] dev %d lane %d loci %6d  h2d %.2f-%.2f  fill %.2f-%.2f  f3 -%.2f  pack -%.2f  d2h -%.2f\n", D.id,
+                    (int)(&Ln - D.lane), nl, t[0], t[1], t[2], t[3], t[4], t[5], t[6]);
+        }
         if (J.sink == SINK_NONE) return true;
         if (J.sink == SINK_CAND) { retire_candidates(Ln); return true; }
         const unsigned long long *h_bounds = Ln.h_out.as<unsigned long long>();
@@ -1442,7 +1452,7 @@ int mirfold_debug_matrices(mirfold_ctx *ctx, const char *seq, uint32_t n, int sp
     const unsigned long long ring_elems = build_fill_units(&d, 1, units, bucket_first, max_n);
     const int nu = (int)units.size();
     CK(Ln.raw.ensure(n)); CK(Ln.loci.ensure(sizeof d)); CK(Ln.codes.ensure(n + 3)); CK(Ln.F.ensure((n + 3) * 4));
-    CK(Ln.C.ensure(cells * 4)); CK(Ln.M.ensure(cells * 4)); CK(Ln.Mp.ensure(cells * 4 + 4096));
+    CK(Ln.C.ensure(cells * 4)); CK(Ln.M.ensure(cells * 4)); CK(Ln.Mp.ensure(cells * 4 + 4096)); CK(Ln.Ib.ensure(cells + 256));
     CK(Ln.ring.ensure((size_t)ring_elems * 4));
     CK(Ln.units.ensure(sizeof(LocusDesc) * (size_t)nu + 64));
     CK(cudaMemcpyAsync(Ln.raw.p, seq, n, cudaMemcpyHostToDevice, st));
@@ -1453,7 +1463,7 @@ int mirfold_debug_matrices(mirfold_ctx *ctx, const char *seq, uint32_t n, int sp
     CK(Ln.fillflags.ensure((size_t)nu * 4 + 4));
     CK(cudaMemsetAsync(Ln.fillflags.p, 0, (size_t)nu * 4 + 4, st));
     FillLaunch fa{Ln.units.as<LocusDesc>(), nu, max_n, Ln.codes.as<unsigned char>(), Ln.C.as<int>(), Ln.M.as<int>(), Ln.ring.as<int>(),
-                  Ln.Mp.as<unsigned int>(), D.dP, {0, 0, 0, 0, 0}, Ln.fillflags.as<int>(),
+                  Ln.Ib.as<unsigned char>(), Ln.Mp.as<unsigned int>(), D.dP, {0, 0, 0, 0, 0}, Ln.fillflags.as<int>(),
                   ((flags & MIRFOLD_FLAG_WIDE) || span_L > MF16_MAX_SPAN) ? 1 : 0, env_opts()};
     for (int b = 0; b < 5; b++) fa.bucket_first[b] = bucket_first[b];
     CK(launch_fill(fa, st));

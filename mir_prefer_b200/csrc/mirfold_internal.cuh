@@ -123,6 +123,7 @@ struct FillLaunch {
     int max_n;
     const unsigned char *codes;
     int *C, *M, *ring;
+    unsigned char *Ib;    // one byte per band cell: "some two-loop candidate reproduces c(i,j)" (traceback hint; all ones from the wide kernels)
     unsigned int *Mp;     // narrow kernel: fML as 16-bit row pairs (locus at band_off; layout by bucket, see dev_store_fml16)
     const DevParams *P;
     int bucket_first[5];  // loci sorted by descending n: [generic | <=608 | <=352 | <=160 | end)
@@ -143,6 +144,7 @@ struct TraceBuffers {
     int nloci;
     const unsigned char *codes;
     const int *C, *M, *F;
+    const unsigned char *Ib;       // traceback hint bytes of the fill (FillLaunch::Ib)
     const DevParams *P;
     // plan
     int *tb_count;                 // nloci

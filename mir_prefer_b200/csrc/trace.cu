@@ -62,6 +62,7 @@ struct Fold {
     const int *__restrict__ C;
     const int *__restrict__ M;
     const int *__restrict__ F;
+    const unsigned char *__restrict__ Ib;  // hint bytes, same cell addressing as C
     const unsigned char *pairT;   // shared-memory copies of DevParams::pair / rtype (block-wide)
     const unsigned char *rtypeT;
     int AUp;                      // TerminalAU
@@ -85,6 +86,14 @@ struct Fold {
         unsigned long long off = (unsigned)((d - 4) * NS + (i - 1));
         if (tile_last) off = tb_tiled_off(i, d, tile_rcp, tile_last, tile_step, n, dmax);
         return C[off];
+    }
+    // fill's hint for the pair (i,j): false = no two-loop (p,q) reproduces c(i,j), the candidate scan cannot succeed
+    __device__ __forceinline__ bool two_loop_possible(int i, int j) const
+    {
+        const int d = j - i;
+        unsigned long long off = (unsigned)((d - 4) * NS + (i - 1));
+        if (tile_last) off = tb_tiled_off(i, d, tile_rcp, tile_last, tile_step, n, dmax);
+        return Ib[off] != 0;
     }
     __device__ __forceinline__ int band(const int *__restrict__ A, int i, int j) const
     {
@@ -167,6 +176,7 @@ __global__ void __launch_bounds__(128, TB_MINB) k_traceback(TraceBuffers b)
     const int start = b.tb_start_list[b.list_off[l] + kidx];
     Fold f;
     f.P = b.P; f.C = b.C + L.band_off; f.M = b.M + L.band_off; f.F = b.F + L.seq_off;
+    f.Ib = b.Ib + L.band_off;
     f.pairT = sPairT; f.rtypeT = sRtypeT; f.AUp = b.P->TerminalAU;
     f.n = L.n; f.Ls = L.Ls; f.NS = L.stride;
     f.tile_last = L.tile_last; f.tile_step = L.tile_step; f.dmax = L.dmax; f.tile_rcp = L.tile_rcp;
@@ -343,7 +353,7 @@ __global__ void __launch_bounds__(128, TB_MINB) k_traceback(TraceBuffers b)
             const int K = min(30, d - 6);
             int np = 0, nq = 0;
             bool found = false;
-            if (K >= 0) {
+            if (K >= 0 && f.two_loop_possible(i, j)) {
                 for (int cb = 0; cb < 496 && !found; cb += 32 * TB_UNR) {
                     bool ok[TB_UNR];
                     int p[TB_UNR], q[TB_UNR];
