@@ -180,6 +180,13 @@ int mirfold_format_records(const mirfold_result *res, const char *seqs, const ui
                            char **text, uint64_t **rec_off);
 void mirfold_free_text(char *text, uint64_t *rec_off);
 
+/* Replaces: one whole `RNALfold -L span_L < text > out` run (miR_PREFeR.py:3053, :3064) -- RNALfold's main() in one call:
+ * lines starting with '>' or '*' and empty lines are echoed, a line "@" ends the input, the first whitespace-delimited
+ * token of any other line is folded and its record block printed.  *out holds *out_len bytes, byte-identical
+ * to RNALfold's stdout; release with mirfold_free_text(*out, NULL). */
+int mirfold_fold_text(mirfold_ctx *ctx, const char *text, uint64_t len, int span_L, uint32_t flags, char **out,
+                      uint64_t *out_len);
+
 /* Replaces: the structure classification of get_structures_next_extendregion (miR_PREFeR.py:1566-1589) with
  * is_stem_loop (:1602), filter_ss (:1685) and has_one_good_bifurcation (:1611): for every hit of at least
  * `minlen` characters the candidate structures the predict stage consumes -- the whole hairpin (sstype 0) or

@@ -89,7 +89,7 @@ EXPORTS = ["mirfold_open", "mirfold_close", "mirfold_fold", "mirfold_fold_device
            "mirfold_free_result", "mirfold_strerror", "mirfold_last_error", "mirfold_version", "mirfold_duplex",
            "mirfold_duplex_fail_name", "mirfold_int_peak", "mirfold_format_records", "mirfold_free_text",
            "mirfold_classify", "mirfold_free_structures", "mirfold_fold_stream", "mirfold_batch_upload", "mirfold_batch_fold",
-           "mirfold_batch_free", "mirfold_plan_shards", "mirfold_int_peak2", "mirfold_fold_candidates", "mirfold_free_candidates"]
+           "mirfold_batch_free", "mirfold_plan_shards", "mirfold_int_peak2", "mirfold_fold_candidates", "mirfold_free_candidates", "mirfold_fold_text"]
 
 _lib = None
 
@@ -154,9 +154,11 @@ def load():
     lib.mirfold_plan_shards.argtypes = [C.POINTER(C.c_uint64), C.c_uint32, C.c_int, C.c_int, C.POINTER(C.c_uint32),
                                         C.POINTER(C.c_uint64)]
     lib.mirfold_plan_shards.restype = C.c_int
-    if os.environ.get("MIRFOLD_LIB_PATH") and not hasattr(lib, "mirfold_fold_candidates"):
+    if os.environ.get("MIRFOLD_LIB_PATH") and not all(hasattr(lib, x) for x in ("mirfold_fold_candidates", "mirfold_fold_text")):
         _lib = lib      # an older A/B build of the library: the entry points below are not in it
         return lib
+    lib.mirfold_fold_text.argtypes = [vp, C.c_char_p, C.c_uint64, C.c_int, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+    lib.mirfold_fold_text.restype = C.c_int
     lib.mirfold_fold_candidates.argtypes = [vp, C.c_void_p, C.POINTER(C.c_uint64), C.c_uint32, C.c_int, C.c_uint32, C.c_void_p,
                                             C.c_void_p, C.POINTER(C.c_uint64), C.c_int, C.c_int, C.c_int, C.c_int,
                                             C.POINTER(C.POINTER(Candidates))]

@@ -394,13 +394,12 @@ __device__ __forceinline__ void dev_phase_a16_sys(const unsigned int *Mp, int *r
             for (int s = 0; s < 5; s++) {
                 const int lo = (int)(short)(acc[s] & 0xffffu), hi = (int)acc[s] >> 16;
                 int *dst = &rD[((d + s) & (MF_RING_DML - 1)) * NS + (i - 1)];
-                if (s < ns && lo < MF16M_VALID) {
-                    if (nparts == 1) dst[0] = lo;
-                    else atomicMin(dst, lo);
-                }
-                if (s < nsh && hi < MF16M_VALID) {
-                    if (nparts == 1) dst[1] = hi;
-                    else atomicMin(dst + 1, hi);
+                if (nparts == 1) {   // the only writer of these cells: no preset needed (see the ring reset in k_fill_s16)
+                    if (s < ns) dst[0] = lo < MF16M_VALID ? lo : MF_INF;
+                    if (s < nsh) dst[1] = hi < MF16M_VALID ? hi : MF_INF;
+                } else {
+                    if (s < ns && lo < MF16M_VALID) atomicMin(dst, lo);
+                    if (s < nsh && hi < MF16M_VALID) atomicMin(dst + 1, hi);
                 }
             }
         }
@@ -527,13 +526,12 @@ __device__ __forceinline__ void dev_phase_a16_sysx(const unsigned int *Mp, int *
             for (int s = 0; s < 5; s++) {
                 const int lo = (int)(short)(acc[s] & 0xffffu), hi = (int)acc[s] >> 16;
                 int *dst = &rD[((d + s) & (MF_RING_DML - 1)) * NS + (i - 1)];
-                if (s < ns && lo < MF16M_VALID) {
-                    if (nparts == 1) dst[0] = lo;
-                    else atomicMin(dst, lo);
-                }
-                if (s < nsh && hi < MF16M_VALID) {
-                    if (nparts == 1) dst[1] = hi;
-                    else atomicMin(dst + 1, hi);
+                if (nparts == 1) {   // the only writer of these cells: no preset needed (see the ring reset in k_fill_s16)
+                    if (s < ns) dst[0] = lo < MF16M_VALID ? lo : MF_INF;
+                    if (s < nsh) dst[1] = hi < MF16M_VALID ? hi : MF_INF;
+                } else {
+                    if (s < ns && lo < MF16M_VALID) atomicMin(dst, lo);
+                    if (s < nsh && hi < MF16M_VALID) atomicMin(dst + 1, hi);
                 }
             }
         }
@@ -732,8 +730,11 @@ __global__ void __launch_bounds__(NT, MINB) k_fill_smem(FillLaunch a)
 // bank class l (DevParams::s16_*), so a typed cell costs 10 conflict-free LDS + 10 VIADDMNMX.S16x2 per
 // lane (8 generic, 2 bulge), one packed combine and one redux.  Exact while c > MF16_GUARD; otherwise
 // the locus is flagged for the 32-bit kernel.
+#ifndef MF16_NWM_DELTA
+#define MF16_NWM_DELTA 0
+#endif
 #ifndef MF16_NWM
-#define MF16_NWM(NT) (((NT) / 32 * 3 + 4) / 8)   /* fML/list warps of the narrow kernel: 6 of 16, 5 of 12, 3 of 8 */
+#define MF16_NWM(NT) (((NT) / 32 * 3 + 4) / 8 - MF16_NWM_DELTA)   /* fML/list warps of the narrow kernel: 6 of 16, 4 of 10, 3 of 8 */
 #endif
 template <int NS>
 struct Fill16Smem {
@@ -747,27 +748,43 @@ struct Fill16Smem {
 // Byte offset (from the start of sG) of the word-term `td` of lane `lane` for a cell on diagonal d.
 // A lane without a term in this iteration reads the all-INF row at the bank its own class would use,
 // which no other lane touches in the same instruction.
-__device__ __forceinline__ unsigned dev_term_off16(unsigned td, int lane, int d, int RS, int RW)
+// Word offset of pair slot pp's row inside a ring: (pp % 17) * RS + ((17 pp) & 31).  The modulo is not cheap and every ring
+// access of the thread-per-cell phases needs it for two or three diagonals, so the kernel keeps the values of the live pairs in
+// a 32-entry shared table (entry pp & 31; one thread adds the next pair per diagonal) -- fML -20 %, word-term offsets -60 %
+// instructions (profiles/r02_v6_rowtab_ab.txt).
+struct RingRows {
+    const int *tab;
+    int RS;
+    __device__ __forceinline__ int operator()(int pp) const
+    {
+#ifdef MF_NO_ROWTAB
+        return (pp % MF16_NPS) * RS + ((MF16_SKEW * pp) & 31);
+#else
+        return tab[pp & 31];
+#endif
+    }
+    static __device__ __forceinline__ int direct(int pp, int RS_) { return (pp % MF16_NPS) * RS_ + ((MF16_SKEW * pp) & 31); }
+};
+
+__device__ __forceinline__ unsigned dev_term_off16(unsigned td, int lane, int d, RingRows rr, int RS, int RW)
 {
     const int ppb = (d - 2) >> 1;
     if (td >> 11) return (unsigned)(MF16_NPS * RS + ((lane + MF16_SKEW * ppb) & 31)) * 4u;
     const int m = td & 15, xo = (td >> 4) & 63, pp = ppb - m;
-    const int row = pp < 0 ? MF16_NPS * RS : (pp % MF16_NPS) * RS + ((MF16_SKEW * pp) & 31);   // pp < 0: all-INF row (d < 34 only)
+    const int row = pp < 0 ? MF16_NPS * RS : rr(pp);   // pp < 0: all-INF row (d < 34 only)
     return (unsigned)(((td >> 10) & 1) * RW + row + xo) * 4u;
 }
-__device__ __forceinline__ void dev_ring16_put(unsigned int *ring, int RS, int d, int x, int v)
+__device__ __forceinline__ void dev_ring16_put(unsigned int *ring, RingRows rr, int d, int x, int v)
 {
-    const int pp = d >> 1;
-    unsigned short *w = (unsigned short *)(ring + (pp % MF16_NPS) * RS + ((MF16_SKEW * pp) & 31) + x);
+    unsigned short *w = (unsigned short *)(ring + rr(d >> 1) + x);
     w[d & 1] = (unsigned short)v;
 }
 
 
 // 16-bit ring read: value of diagonal dd at row index x (= p-1)
-__device__ __forceinline__ int dev_ring16_get(const unsigned int *ring, int RS, int dd, int x)
+__device__ __forceinline__ int dev_ring16_get(const unsigned int *ring, RingRows rr, int dd, int x)
 {
-    const int pp = dd >> 1;
-    const short *w = (const short *)(ring + (pp % MF16_NPS) * RS + ((MF16_SKEW * pp) & 31) + x);
+    const short *w = (const short *)(ring + rr(dd >> 1) + x);
     return w[dd & 1];
 }
 
@@ -777,7 +794,7 @@ __device__ __forceinline__ int dev_ring16_get(const unsigned int *ring, int RS, 
 template <class StrideT>
 __device__ __forceinline__ int dev_cell_tail16(const DevParams *__restrict__ P, const unsigned char *sS,
                                                const unsigned char *sS1, const unsigned char *sPair,
-                                               const unsigned int *sB, int RS, const int *rD, StrideT NS, int i,
+                                               const unsigned int *sB, RingRows RS, const int *rD, StrideT NS, int i,
                                                int d, int t, int si1, int sj1, int K, int &two_loop_min)
 {
     const int j = i + d;
@@ -822,7 +839,7 @@ __device__ __forceinline__ int dev_cell_tail16(const DevParams *__restrict__ P, 
 // the only global read is DML(i,j).
 template <class StrideT>
 __device__ __forceinline__ int dev_fml16(const DevParams *__restrict__ P, const unsigned char *sS, const unsigned char *sS1,
-                                         const unsigned char *sPair, const unsigned int *sB, int RS, const int *Mprev,
+                                         const unsigned char *sPair, const unsigned int *sB, RingRows RS, const int *Mprev,
                                          const int *rD, StrideT NS, int i, int d, int Ls)
 {
     const int j = i + d;
@@ -876,12 +893,15 @@ __global__ void __launch_bounds__(NT, MINB) k_fill_s16(FillLaunch a)
     unsigned char *sPair = sS1 + NS + 8;                      // [64]
     __shared__ int sCount[3];
     __shared__ int sFlag;
+    __shared__ int sRowP[32];                                 // ring row (words) of pair slot pp at [pp & 31]
+    const RingRows rr{sRowP, RS};
 
     const LocusDesc L = a.loci[blockIdx.x];
     const int n = L.n, Ls = L.Ls, dmax = L.dmax;
     const DevParams *__restrict__ P = a.P;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int AUp = P->TerminalAU;
+    if (tid < 32) sRowP[tid] = RingRows::direct(tid, RS);
 
     for (int k = tid; k < NS + 8; k += NT) {
         const unsigned char b = (k < n + 3) ? a.codes[L.seq_off + k] : 0;
@@ -895,7 +915,6 @@ __global__ void __launch_bounds__(NT, MINB) k_fill_s16(FillLaunch a)
     if (tid == 0) sFlag = 0;
     for (int k = tid; k < 2 * MF16_NQ * 32; k += NT) sCst[k] = (&P->s16_cst[0][0][0])[k];
     for (int k = tid; k < 2 * MF16_NMK * 32; k += NT) sMk[k] = (&P->s16_mk[0][0][0])[k];
-    for (int k = tid; k < MF16_NQ * 32; k += NT) sOff[k] = dev_term_off16((&P->s16_td[0][0][0])[k], k & 31, 4, RS, RW);
 
     int *Cb = a.C + L.band_off;
     int *Mb = a.M + L.band_off;
@@ -914,6 +933,8 @@ __global__ void __launch_bounds__(NT, MINB) k_fill_s16(FillLaunch a)
     for (int k = tid; k < MF_RING_DML * NS; k += NT) rD[k] = MF_INF;
     __syncthreads();
 
+    // word-term offsets of the first diagonal (the row table is ready now)
+    for (int k = tid; k < MF16_NQ * 32; k += NT) sOff[k] = dev_term_off16((&P->s16_td[0][0][0])[k], k & 31, 4, rr, RS, RW);
     // typed list / untyped INF of the first diagonal
     if (dmax >= 4) {
         for (int i = tid + 1; i <= n - 4; i += NT) {
@@ -1003,7 +1024,7 @@ __global__ void __launch_bounds__(NT, MINB) k_fill_s16(FillLaunch a)
                     const int si1 = sS1[i + 1], sj1 = sS1[j - 1];
                     const int wide_loops = (my < MF16_VALID) ? my + sMM[(t * 5 + si1) * 5 + sj1] : MF_INF;
                     int small_loops;
-                    const int best = min(wide_loops, dev_cell_tail16(P, sS, sS1, sPair, sB, RS, rD, NS, i, d, t, si1, sj1, K, small_loops));
+                    const int best = min(wide_loops, dev_cell_tail16(P, sS, sS1, sPair, sB, rr, rD, NS, i, d, t, si1, sj1, K, small_loops));
                     const int tt = dev_rtype(t);
                     const int mm = sMM[(tt * 5 + sS1[j + 1]) * 5 + sS1[i - 1]];
                     Cb[(d - 4) * NS + i - 1] = best;
@@ -1011,8 +1032,8 @@ __global__ void __launch_bounds__(NT, MINB) k_fill_s16(FillLaunch a)
                     // 496-candidate scan and goes straight to the multiloop decomposition (58 % of its scan rounds end there)
                     Ib[(d - 4) * NS + i - 1] = (unsigned char)(min(wide_loops, small_loops) == best);
                     if (best < MF16_GUARD) sFlag = 1;
-                    dev_ring16_put(sG, RS, d, i - 1, max(best + mm, -32768));
-                    dev_ring16_put(sB, RS, d, i - 1, max(best + (tt > 2 ? AUp : 0), -32768));
+                    dev_ring16_put(sG, rr, d, i - 1, max(best + mm, -32768));
+                    dev_ring16_put(sB, rr, d, i - 1, max(best + (tt > 2 ? AUp : 0), -32768));
                 }
             } else asm volatile("bar.sync 1, %0;" ::"n"(CT) : "memory");
         } else {
@@ -1025,7 +1046,7 @@ __global__ void __launch_bounds__(NT, MINB) k_fill_s16(FillLaunch a)
                 const int *Mprev = sMrow + ((dm - 1) & 1) * NS;
                 int *Mcur = sMrow + (dm & 1) * NS;
                 for (int i = mt + 1; i <= n - dm; i += MT) {
-                    const int m = dev_fml16(P, sS, sS1, sPair, sB, RS, Mprev, rD, NS, i, dm, Ls);
+                    const int m = dev_fml16(P, sS, sS1, sPair, sB, rr, Mprev, rD, NS, i, dm, Ls);
                     if (!BULK) Mb[(dm - 4) * NS + i - 1] = m;
                     Mcur[i - 1] = m;
                     dev_store_fml16_sel<OC>(Mp, NS, dm, i, m, &sFlag);   // 16-bit copy (copies) for the DML strips
@@ -1042,17 +1063,23 @@ __global__ void __launch_bounds__(NT, MINB) k_fill_s16(FillLaunch a)
                         const int dl = (t > 2 ? AUp : 0) - sMM[(t * 5 + sS1[i + 1]) * 5 + sS1[i + dn - 1]] + MF16_DBIAS;
                         list[atomicAdd(&sCount[dn % 3], 1)] = (unsigned)(i * 4) | ((unsigned)dl << 16);
                     } else {
-                        dev_ring16_put(sG, RS, dn, i - 1, MF16_INF);
-                        dev_ring16_put(sB, RS, dn, i - 1, MF16_INF);
+                        dev_ring16_put(sG, rr, dn, i - 1, MF16_INF);
+                        dev_ring16_put(sB, rr, dn, i - 1, MF16_INF);
                         Cb[(dn - 4) * NS + i - 1] = MF_INF;
                     }
                 }
                 for (int k = mt; k < MF16_NQ * 32; k += MT)
-                    sOff[(dn & 1) * MF16_NQ * 32 + k] = dev_term_off16((&P->s16_td[dn & 1][0][0])[k], k & 31, dn, RS, RW);
+                    sOff[(dn & 1) * MF16_NQ * 32 + k] = dev_term_off16((&P->s16_td[dn & 1][0][0])[k], k & 31, dn, rr, RS, RW);
             }
+            if (mt == MT - 1) sRowP[((it + 3) >> 1) & 31] = RingRows::direct((it + 3) >> 1, RS);   // first used for diagonal it+2
             if ((it + 1 - 5) % 5 == 0 && it <= dmax) {   // next iteration runs the DML strip [it, it+4]
-                for (int s = 0; s < 5; s++)
-                    for (int i = mt; i < n; i += MT) rD[((it + s) & (MF_RING_DML - 1)) * NS + i] = MF_INF;
+                // a strip whose rows are not split over several warps (nparts == 1) overwrites every cell it owns; only the
+                // atomicMin accumulation of split rows needs the ring rows preset
+                constexpr int TWs = OC ? 30 : 29;
+                const int ntiles = (((n - it + 1) >> 1) + TWs - 1) / TWs;
+                if (NW / ntiles > 1)
+                    for (int s = 0; s < 5; s++)
+                        for (int i = mt; i < n; i += MT) rD[((it + s) & (MF_RING_DML - 1)) * NS + i] = MF_INF;
             }
         }
         TL_MARK(3)

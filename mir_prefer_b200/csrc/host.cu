@@ -543,6 +543,22 @@ struct DevicePipeline {
             acc += lb[k];
         }
         chunks.push_back({b, loci.size()});
+        // The download of a device's LAST chunk is the only one nothing overlaps (154 MB per device take 11.6 ms when eight GPUs
+        // write into host memory at once): cut the last chunk 80 : 20 so that only the small tail's download is exposed.
+        if (J.sink != SINK_NONE) {
+            const Chunk last = chunks.back();
+            uint64_t cells = 0;
+            for (size_t k = last.begin; k < last.end; k++) cells += loci[k].cells;
+            if (cells > 100000000ull && last.end - last.begin >= 64) {
+                uint64_t acc2 = 0;
+                size_t cut = last.begin;
+                while (cut < last.end && acc2 < cells - cells / 5) acc2 += loci[cut++].cells;
+                if (cut > last.begin && cut < last.end) {
+                    chunks.back().end = cut;
+                    chunks.push_back({cut, last.end});
+                }
+            }
+        }
     }
 
     // ---- front: descriptors, upload, encode, band fill, f3, emission plan (everything up to the first host sync)

@@ -527,9 +527,23 @@ class MirFold:
 
     # ---- RNALfold CLI contract -------------------------------------------------------------
     def fold_text_bytes(self, text, span, encoding=None):
-        """RNALfold-identical stdout (bytes) for RNALfold-style stdin text (`RNALfold -L span`).  `encoding`:
-        how echoed header lines go back to bytes (default utf-8 with surrogateescape; "latin-1" for text that was
-        decoded from raw bytes as latin-1)."""
+        """RNALfold-identical stdout (bytes) for RNALfold-style stdin text (`RNALfold -L span`), in one native call
+        (mirfold_fold_text: parse, fold, format).  `text` may be bytes; a str is encoded with `encoding` (default utf-8
+        with surrogateescape, so header bytes that were decoded that way come back unchanged)."""
+        if isinstance(text, str):
+            text = text.encode(encoding) if encoding else text.encode("utf-8", "surrogateescape")
+        out, n = C.c_void_p(), C.c_uint64()
+        rc = self._lib.mirfold_fold_text(self._ctx, text, len(text), int(span), 0, C.byref(out), C.byref(n))
+        if rc != 0:
+            self._raise(rc)
+        try:
+            return C.string_at(out, n.value)
+        finally:
+            self._lib.mirfold_free_text(out, None)
+
+    def fold_text_bytes_py(self, text, span, encoding=None):
+        """The same through the Python parser and mirfold_format_records (kept as the readable statement of the I/O contract
+        and as a cross-check of the native path)."""
         items = parse_rnalfold_input(text)
         seqs = [tok for kind, tok in items if kind == "seq"]
         out = []
@@ -567,9 +581,8 @@ class MirFold:
                                 break
                         if not lines:
                             break
-                        text = b"".join(lines).decode("latin-1")
                         stop = any(ln.rstrip(b"\n") == b"@" for ln in lines)     # RNALfold stops reading at '@'
-                        fout.write(self.fold_text_bytes(text, span, encoding="latin-1"))
+                        fout.write(self.fold_text_bytes(b"".join(lines), span))
                         if stop:
                             break
                 os.rename(tmp, outname)   # atomic, like MP:3098

@@ -19,13 +19,14 @@ def _last(pattern):
 
 
 def test_committed_bench_line_has_every_contract_key():
-    d = _last("r01_v*_bench.json")
+    d = _last("r02_v*_bench.json")
     assert BASE_KEYS <= set(d) and {"roofline", "cpu_baseline", "clocks"} <= set(d)
     assert d["metric"].startswith("folded nt/sec") and d["unit"] == "nt/s" and d["higher_is_better"] is True
-    assert d["scaling"] == "weak" and d["data"] == "synthetic" and d["vs_baseline"] is None
-    assert "workload" in d["config"] and "model" not in d["config"]
+    assert d["scaling"] == "strong" and d["data"] == "synthetic" and d["vs_baseline"] is None
+    assert "workload" in d["config"] and "model" not in d["config"] and "configs[2]" in d["config"]["workload"]
     assert d["n_gpus"] == 1 and d["warmup"] >= 3 and d["gpu_launches"] > 0
-    assert abs(d["value"] - d["config"]["nt_per_gpu"] / (d["ms_per_step"] * 1e-3)) / d["value"] < 1e-6
+    assert abs(d["value"] - d["config"]["nt"] / (d["ms_per_step"] * 1e-3)) / d["value"] < 1e-6
+    assert d["parity_in_run"]["equal"] is True and d["parity_in_run"]["text_bytes"] == 1235240762
     e = d["e2e"]
     assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(e)
     assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["value"] < d["value"]
@@ -38,8 +39,20 @@ def test_committed_bench_line_has_every_contract_key():
     assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
 
 
+def test_committed_multi_gpu_lines_are_strong_scaling_through_one_context():
+    one = _last("r02_v*_bench.json")
+    for n in (2, 4, 8):
+        d = _last("r02_v*_bench_%dgpu.json" % n)
+        assert d["n_gpus"] == n and d["scaling"] == "strong" and d["config"]["devices"] == n
+        assert d["config"]["nt"] == one["config"]["nt"]                       # the same job on more GPUs
+        assert d["parity_in_run"]["equal"] is True                           # the multi-device result is the RNALfold text
+        assert d["sharding"]["lpt_imbalance"] < 1.001
+        assert d["e2e"]["value"] < d["value"] and d["weak"]["scaling"] == "weak"
+        assert d["value"] > 0.85 * n * one["value"]                          # resident strong-scaling efficiency
+
+
 def test_committed_reference_line():
-    d = _last("r01_v*_bench_reference.json")
+    d = _last("r02_v*_bench_reference.json")
     assert d["impl"] == "reference" and BASE_KEYS <= set(d)
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
     assert d["cpu_baseline"]["value"] == d["value"] and d["gpu_launches"] == 0

@@ -187,6 +187,23 @@ def test_full_size_configs_match_rnalfold_sha256(mf, pin):
     assert hashlib.sha256(out.encode()).hexdigest() == pin["sha256"]
 
 
+def test_native_text_path_equals_python_path(mf):
+    """mirfold_fold_text (parse + fold + format natively) == the Python parser + mirfold_format_records, byte for byte, on the
+    golden inputs and on awkward text: no final newline, '@' terminator, tabs / CR / blank-only lines, '*' lines, raw bytes."""
+    for name in ("edge", "alphabet", "synth8"):
+        text = open(os.path.join(GOLDEN, name + ".in")).read()
+        for L in (30, 300):
+            assert mf.fold_text_bytes(text, L) == mf.fold_text_bytes_py(text, L), (name, L)
+    odd = ">h1 x\r\nGGGGAAAACCCC extra tokens\n\n   \n\tacgtacgtac\r\n*note\n>caf\u00e9\nACGUNNNACGU\n@\n>never\nGGGG\n"
+    assert mf.fold_text_bytes(odd, 300) == mf.fold_text_bytes_py(odd, 300)
+    assert b">never" not in mf.fold_text_bytes(odd, 300)
+    tail = ">a\nGGGGGTTTTCCCCC"                           # no newline at the end
+    assert mf.fold_text_bytes(tail, 300) == mf.fold_text_bytes_py(tail, 300)
+    assert mf.fold_text_bytes(b"", 300) == b"" and mf.fold_text_bytes(b"\n", 300) == b"\n"
+    raw = b">x\xff\xfe\nACGTACGTAA\n"
+    assert mf.fold_text_bytes(raw, 300).startswith(b">x\xff\xfe\n")
+
+
 def test_native_formatter_equals_python_formatter(mf):
     """mirfold_format_records() (C, multi-threaded) vs the Python format_record() on every record, including
     empty / tiny records, lower case and IUPAC letters, and more than 256 records (threaded path)."""

@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2 final 1-GPU pass: parity suite, the bench line of record + reference arm, secondary workloads, span sweep with ncu,
+# round 2, 1-GPU pass (bash tools/gpu_round2.sh TAG through gpurun): parity suite, the bench line of record + reference arm, secondary workloads, span sweep with ncu,
 # launch list and ncu --set full of the dominant kernel
 TAG=${1:-k}
 mkdir -p gpurun_out
@@ -26,9 +26,12 @@ for f in ("bench","bench_parity","bench_long","bench_sweep_L150","bench_sweep_L3
 PY
 # ncu: span sweep (smem vs L2 throughput of the fill kernel per span), then the launch list and the full capture of the bench's own kernel
 export MIRFOLD_CHUNK_CELLS=1e12 MIRFOLD_SERIAL=1
+if [ -n "$SWEEP_NCU" ]; then
 for L in 150 300 500; do
   timeout 600 ncu --set full --clock-control none -k regex:k_fill_s16 -s 2 -c 2 -o gpurun_out/r02_prof_sweep_L${L}_$TAG -f python bench.py --workload sweep --loci 3000 --span $L --steps 1 --warmup 1 --no-cpu --no-sha --no-dropin > gpurun_out/r02_prof_sweep_L${L}_$TAG.log 2>&1
 done
+fi
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_traceback -s 1 -c 1 -o gpurun_out/r02_prof_tb_$TAG -f python bench.py --loci 20000 --steps 1 --warmup 1 --no-cpu --no-sha --no-dropin > gpurun_out/r02_prof_tb_$TAG.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_fill_s16 -s 1 -c 1 -o gpurun_out/r02_prof_fill352_$TAG -f python bench.py --loci 20000 --steps 1 --warmup 1 --no-cpu --no-sha --no-dropin > gpurun_out/r02_prof_fill_$TAG.log 2>&1
 unset MIRFOLD_CHUNK_CELLS MIRFOLD_SERIAL
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/r02_launches_$TAG.csv python bench.py --loci 40000 --steps 2 --warmup 1 --no-cpu --no-sha --no-dropin > gpurun_out/r02_b_ncu_$TAG.log 2>&1
