@@ -450,6 +450,7 @@ struct DevicePipeline {
     std::vector<Locus> loci;      // descending DP cells
     struct Chunk { size_t begin, end; };
     std::vector<Chunk> chunks;
+    int nlanes_ = 1;
     HostTimer ht;
 
     DevicePipeline(Device &D_, const Job &J_, const char *d_raw_, const uint64_t *raw_off_, DevOut &out_)
@@ -487,7 +488,7 @@ struct DevicePipeline {
         plan_chunks(total_cells);
         out.st.n_chunks = (int32_t)chunks.size();
         ht.mark("plan chunks");
-        const int nlanes = (J.serial || chunks.size() < 2) ? 1 : 2;
+        const int nlanes = nlanes_ = (J.serial || chunks.size() < 2) ? 1 : 2;
         bool ok = true;
         if (!chunks.empty()) {
             CK(cudaEventRecord(D.ev_first, D.lane[0].s_lo));
@@ -633,6 +634,11 @@ struct DevicePipeline {
         CK(cudaMemsetAsync(Ln.fail.p, 0, 4, lo));
         CK(cudaMemsetAsync(Ln.fillflags.p, 0, (size_t)nu * 4 + 4, lo));
         CK(cudaEventRecord(Ln.ev[1], lo));
+        // The two lanes' fills normally share the SMs and finish together, which is what hides wave tails -- but it also means the
+        // small last chunk (plan_chunks cuts it 80 : 20) would be done before the previous chunk's download even starts.  Its fill
+        // therefore waits for the previous chunk's fill to END: it then runs next to that chunk's traceback and under its download.
+        if (J.sink != SINK_NONE && nlanes_ == 2 && ci > 0 && ci + 1 == chunks.size())
+            CK(cudaStreamWaitEvent(lo, D.lane[(ci + 1) % 2].ev[3], 0));
         // ---- K1, K2 on the low-priority stream
         const LocusDesc *dl = Ln.loci.as<LocusDesc>();
         CK(launch_prepare(raw_dev, dl, nl, P.seq_acc, Ln.codes.as<unsigned char>(), Ln.F.as<int>(), lo));
