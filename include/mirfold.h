@@ -77,7 +77,7 @@ typedef struct mirfold_stats {
     uint64_t h2d_bytes, d2h_bytes;
     int32_t n_devices;
     int32_t n_chunks;
-    uint64_t fill_units;  /* CTAs of the band fill: one per locus, one per 608-nt tile of a longer locus */
+    uint64_t fill_units;  /* CTAs of the band fill: one per locus, one per tile of a longer locus (mirfold_plan_fill_units) */
 } mirfold_stats;
 
 /* Result of folding `nseq` records.  Hit order inside a record == RNALfold print order. */
@@ -168,6 +168,24 @@ void mirfold_batch_free(mirfold_batch *batch);
  * shard_cells[g] = DP cells assigned to shard g (either output may be NULL). */
 int mirfold_plan_shards(const uint64_t *seq_off, uint32_t nseq, int span_L, int n_shards, uint32_t *shard_of,
                         uint64_t *shard_cells);
+
+/* How the band fill cuts one locus of n bases at span span_L into fill units (one CTA each).  The reference has no
+ * counterpart (RNALfold walks a locus row by row, Lfold.c:189-346); exported so that callers and tests can reason about
+ * memory and work per locus.  Host-only.  A locus longer than the largest shared-memory bucket is filled as n_units
+ * overlapping tiles of tile_len bases: tile t covers bases a_t+1 .. a_t+tile_len, a_t = min(t*tile_step, n-tile_len),
+ * and owns rows a_t+1 .. a_t+tile_step (the last tile: all its remaining rows); every cell (i, j <= i+span) of an owned
+ * row lies inside the tile.  kernel: 0 = generic global-memory kernel, else the shared-memory bucket's stride
+ * (160 / 352 / 608 / 864).  band_cells = cells the band arrays hold (stride * diagonals * n_units). */
+typedef struct mirfold_fill_plan {
+    int32_t kernel;
+    int32_t stride;
+    int32_t tile_len;    /* n when the locus is one unit */
+    int32_t tile_step;   /* rows owned per tile; n when the locus is one unit */
+    int32_t n_units;
+    int32_t dmax;        /* widest diagonal of the band: min(span_L, n) capped at n-1 */
+    uint64_t band_cells;
+} mirfold_fill_plan;
+int mirfold_plan_fill_units(uint32_t n, int span_L, mirfold_fill_plan *out);
 
 /* Replaces: what RNALfold's main() prints per record (RLF .rodata "%s (%6.2f) %4d\n" / "%s\n (%6.2f)\n",
  * SURVEY A.6) -- the text miR_PREFeR.py collects at :3085-3098 and parses at :1541-1599.  For every record r

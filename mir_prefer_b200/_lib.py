@@ -84,12 +84,17 @@ class Candidates(C.Structure):
                 ("stats", Stats)]
 
 
+class FillPlan(C.Structure):
+    _fields_ = [("kernel", C.c_int32), ("stride", C.c_int32), ("tile_len", C.c_int32), ("tile_step", C.c_int32),
+                ("n_units", C.c_int32), ("dmax", C.c_int32), ("band_cells", C.c_uint64)]
+
+
 # every symbol include/mirfold.h declares
 EXPORTS = ["mirfold_open", "mirfold_close", "mirfold_fold", "mirfold_fold_device", "mirfold_debug_matrices",
            "mirfold_free_result", "mirfold_strerror", "mirfold_last_error", "mirfold_version", "mirfold_duplex",
            "mirfold_duplex_fail_name", "mirfold_int_peak", "mirfold_format_records", "mirfold_free_text",
            "mirfold_classify", "mirfold_free_structures", "mirfold_fold_stream", "mirfold_batch_upload", "mirfold_batch_fold",
-           "mirfold_batch_free", "mirfold_plan_shards", "mirfold_int_peak2", "mirfold_fold_candidates", "mirfold_free_candidates", "mirfold_fold_text"]
+           "mirfold_batch_free", "mirfold_plan_shards", "mirfold_int_peak2", "mirfold_fold_candidates", "mirfold_free_candidates", "mirfold_fold_text", "mirfold_plan_fill_units"]
 
 _lib = None
 
@@ -154,6 +159,9 @@ def load():
     lib.mirfold_plan_shards.argtypes = [C.POINTER(C.c_uint64), C.c_uint32, C.c_int, C.c_int, C.POINTER(C.c_uint32),
                                         C.POINTER(C.c_uint64)]
     lib.mirfold_plan_shards.restype = C.c_int
+    if hasattr(lib, "mirfold_plan_fill_units"):
+        lib.mirfold_plan_fill_units.argtypes = [C.c_uint32, C.c_int, C.POINTER(FillPlan)]
+        lib.mirfold_plan_fill_units.restype = C.c_int
     if os.environ.get("MIRFOLD_LIB_PATH") and not all(hasattr(lib, x) for x in ("mirfold_fold_candidates", "mirfold_fold_text")):
         _lib = lib      # an older A/B build of the library: the entry points below are not in it
         return lib

@@ -1196,6 +1196,9 @@ __global__ void __launch_bounds__(NT) k_fill_generic(FillLaunch a)
 #ifndef MF_B608_NT
 #define MF_B608_NT 512
 #endif
+#ifndef MF_B864_NT
+#define MF_B864_NT 1024    /* stride-864 bucket: 155 KB of shared memory, so one CTA per SM -- it has to bring all 32 warps itself */
+#endif
 #ifndef MF_B352_NT
 #define MF_B352_NT 320     /* threads and CTAs/SM of the stride-352 bucket: 10 warps, 72 registers, no spills (70.5 -> 66.4 ms on 20 k loci of ~306 nt) */
 #define MF_B352_MINB 3
@@ -1211,6 +1214,7 @@ static cudaError_t configure_fill_bucket()
 cudaError_t fill_configure_device()
 {
     cudaError_t e;
+    if ((e = configure_fill_bucket<MF_TILE_LEN_BIG, MF_B864_NT, 1>()) != cudaSuccess) return e;
     if ((e = configure_fill_bucket<608, MF_B608_NT, 2>()) != cudaSuccess) return e;
     if ((e = configure_fill_bucket<352, MF_B352_NT, MF_B352_MINB>()) != cudaSuccess) return e;
     if ((e = configure_fill_bucket<160, 256, 4>()) != cudaSuccess) return e;
@@ -1245,13 +1249,13 @@ cudaError_t launch_fill(const FillLaunch &a, cudaStream_t st, cudaStream_t side,
     cudaError_t e = cudaSuccess;
     // The buckets touch disjoint fill units: the smaller ones run on a side stream so that their CTAs fill
     // the SMs the last wave of the big bucket leaves idle.
-    const bool fork_small = side != nullptr && (a.bucket_first[4] - a.bucket_first[2]) > 0 && (a.bucket_first[2] - a.bucket_first[0]) > 0;
+    const bool fork_small = side != nullptr && (a.bucket_first[5] - a.bucket_first[3]) > 0 && (a.bucket_first[3] - a.bucket_first[0]) > 0;
     cudaStream_t st2 = fork_small ? side : st;
     if (fork_small) {
         if ((e = cudaEventRecord(fork, st)) != cudaSuccess) return e;
         if ((e = cudaStreamWaitEvent(side, fork, 0)) != cudaSuccess) return e;
     }
-    // generic (n > 608)
+    // generic (units no shared-memory bucket holds)
     const int ng = a.bucket_first[1] - a.bucket_first[0];
     if (ng > 0) {
         constexpr int NT = 512;
@@ -1264,9 +1268,10 @@ cudaError_t launch_fill(const FillLaunch &a, cudaStream_t st, cudaStream_t side,
         k_fill_generic<NT><<<ng, NT, smem, st>>>(b);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
-    if ((e = launch_fill_bucket<608, MF_B608_NT, 2>(a, a.bucket_first[1], a.bucket_first[2] - a.bucket_first[1], st)) != cudaSuccess) return e;
-    if ((e = launch_fill_bucket<352, MF_B352_NT, MF_B352_MINB>(a, a.bucket_first[2], a.bucket_first[3] - a.bucket_first[2], st2)) != cudaSuccess) return e;
-    if ((e = launch_fill_bucket<160, 256, 4>(a, a.bucket_first[3], a.bucket_first[4] - a.bucket_first[3], st2)) != cudaSuccess) return e;
+    if ((e = launch_fill_bucket<MF_TILE_LEN_BIG, MF_B864_NT, 1>(a, a.bucket_first[1], a.bucket_first[2] - a.bucket_first[1], st)) != cudaSuccess) return e;
+    if ((e = launch_fill_bucket<608, MF_B608_NT, 2>(a, a.bucket_first[2], a.bucket_first[3] - a.bucket_first[2], st)) != cudaSuccess) return e;
+    if ((e = launch_fill_bucket<352, MF_B352_NT, MF_B352_MINB>(a, a.bucket_first[3], a.bucket_first[4] - a.bucket_first[3], st2)) != cudaSuccess) return e;
+    if ((e = launch_fill_bucket<160, 256, 4>(a, a.bucket_first[4], a.bucket_first[5] - a.bucket_first[4], st2)) != cudaSuccess) return e;
     if (fork_small) {
         if ((e = cudaEventRecord(join, side)) != cudaSuccess) return e;
         if ((e = cudaStreamWaitEvent(st, join, 0)) != cudaSuccess) return e;

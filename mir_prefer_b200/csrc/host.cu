@@ -78,7 +78,7 @@ struct Locus {
 struct Prep {
     size_t cb = 0, ce = 0;   // [cb, ce) into the device's locus list
     int nl = 0, nu = 0, max_n = 0, max_Ls = 0, n_long = 0;
-    int bucket_first[5] = {0, 0, 0, 0, 0};
+    int bucket_first[6] = {0, 0, 0, 0, 0, 0};
     unsigned long long seq_acc = 0, band_acc = 0, raw_acc = 0, list_acc = 0, ring_acc = 0;
 };
 
@@ -365,33 +365,51 @@ cudaError_t exclusive_scan(Lane &Ln, const unsigned long long *in, unsigned long
     return cub::DeviceScan::ExclusiveSum(Ln.scan_tmp.p, tmp, in, out, n, st);
 }
 
-// Band shape of one locus: stride bucket or, for n > MF_TILE_LEN with a span that leaves at least
-// MF_TILE_MIN_STEP owned rows per tile, overlapping tiles for the shared-memory kernels.
+// Band shape of one locus: stride bucket or, for a longer locus with a span that leaves at least
+// MF_TILE_MIN_STEP owned rows per tile, overlapping tiles for the shared-memory kernels.  A tile owns TL - dmax of
+// its TL rows, so wide spans (dmax >= big_tile_min_span(), and every span the 608-nt tile cannot hold) use the
+// 864 bucket: at L = 500 a 608-nt tile owns 108 rows (the locus' cells are computed 3.3 times over), an 864-nt
+// tile 364 (1.4 times); loci of 609..864 nt are then one untiled unit of that bucket.
 // Returns the band elements (per int32 array) the locus occupies.
 #define MF_TILE_MIN_STEP 64
+#ifndef MF_BIG_TILE_MIN_SPAN
+#define MF_BIG_TILE_MIN_SPAN 400
+#endif
+static int big_tile_min_span()
+{
+    static const int v = [] { const char *e = getenv("MIRFOLD_BIG_TILE_MIN_SPAN"); return e ? atoi(e) : MF_BIG_TILE_MIN_SPAN; }();   // A/B runs; a huge value disables the 864 bucket
+    return v;
+}
 unsigned long long shape_locus(LocusDesc &d, int n, int L)
 {
     d.n = n; d.Ls = std::min(L, n); d.dmax = std::min(d.Ls, n - 1);
-    d.stride = band_stride_for(n);
     d.tile_last = 0; d.tile_step = 1 << 30; d.tile_rcp = 0;
     static const bool no_tiles = getenv("MIRFOLD_NO_TILES") != nullptr;   // A/B runs: long loci through k_fill_generic
-    if (n > MF_TILE_LEN && d.dmax >= 4 && MF_TILE_LEN - d.dmax >= MF_TILE_MIN_STEP && !no_tiles) {
-        const int S = MF_TILE_LEN - d.dmax;
-        d.stride = MF_TILE_LEN;
+    const bool big = n > MF_TILE_LEN && d.dmax >= big_tile_min_span() && !no_tiles &&
+                     (n <= MF_TILE_LEN_BIG || MF_TILE_LEN_BIG - d.dmax >= MF_TILE_MIN_STEP);
+    d.stride = band_stride_for(n, big);
+    const int TL = big ? MF_TILE_LEN_BIG : MF_TILE_LEN;
+    if (n > TL && d.dmax >= 4 && TL - d.dmax >= MF_TILE_MIN_STEP && !no_tiles) {
+        const int S = TL - d.dmax;
+        d.stride = TL;
         d.tile_step = S;
-        d.tile_last = (n - MF_TILE_LEN + S - 1) / S;
+        d.tile_last = (n - TL + S - 1) / S;
         d.tile_rcp = (unsigned int)((0x100000000ULL + (unsigned long long)S - 1) / (unsigned long long)S);
-        return (unsigned long long)(d.tile_last + 1) * band_elems(MF_TILE_LEN, d.dmax);
+        return (unsigned long long)(d.tile_last + 1) * band_elems(TL, d.dmax);
     }
     return band_elems(d.stride, d.dmax);
 }
-unsigned long long unit_ring_elems(int n, int stride)
+unsigned long long unit_ring_elems(int stride)
 {
-    return (unsigned long long)stride * (n > MF_TILE_LEN ? MF_RING_PER_STRIDE : MF_RING_DML);
+    return (unsigned long long)stride * (is_bucket_stride(stride) ? MF_RING_DML : MF_RING_PER_STRIDE);
 }
-// Fill units of a chunk: one per untiled locus, one per tile otherwise, sorted by descending n
+static int unit_bucket(const LocusDesc &u)   // index into FillLaunch::bucket_first
+{
+    return !is_bucket_stride(u.stride) ? 0 : u.stride == MF_TILE_LEN_BIG ? 1 : u.stride == MF_TILE_LEN ? 2 : u.stride == 352 ? 3 : 4;
+}
+// Fill units of a chunk: one per untiled locus, one per tile otherwise, sorted by (bucket, descending n)
 // so that the stride buckets are contiguous.  Assigns ring offsets; returns ring elements.
-unsigned long long build_fill_units(const LocusDesc *loci, int nl, std::vector<LocusDesc> &units, int bucket_first[5], int &max_n)
+unsigned long long build_fill_units(const LocusDesc *loci, int nl, std::vector<LocusDesc> &units, int bucket_first[6], int &max_n)
 {
     units.clear();
     max_n = 0;
@@ -401,28 +419,30 @@ unsigned long long build_fill_units(const LocusDesc *loci, int nl, std::vector<L
         if (d.tile_last == 0) { units.push_back(d); continue; }
         for (int t = 0; t <= d.tile_last; t++) {
             LocusDesc u = d;
-            const int a = std::min(t * d.tile_step, d.n - MF_TILE_LEN);
-            u.n = MF_TILE_LEN; u.Ls = std::min(d.Ls, MF_TILE_LEN); u.dmax = d.dmax;
+            const int TL = d.stride;
+            const int a = std::min(t * d.tile_step, d.n - TL);
+            u.n = TL; u.Ls = std::min(d.Ls, TL); u.dmax = d.dmax;
             u.seq_off = d.seq_off + (unsigned long long)a;
-            u.band_off = d.band_off + (unsigned long long)t * band_elems(MF_TILE_LEN, d.dmax);
+            u.band_off = d.band_off + (unsigned long long)t * band_elems(TL, d.dmax);
             u.tile_last = 0;
             units.push_back(u);
         }
     }
-    std::stable_sort(units.begin(), units.end(), [](const LocusDesc &a, const LocusDesc &b) { return a.n > b.n; });
+    std::stable_sort(units.begin(), units.end(), [](const LocusDesc &a, const LocusDesc &b) {
+        const int ba = unit_bucket(a), bb = unit_bucket(b);
+        return ba != bb ? ba < bb : a.n > b.n;
+    });
     unsigned long long ring_acc = 0;
     int k = 0;
     const int nu = (int)units.size();
-    const int lim[3] = {608, 352, 160};
     bucket_first[0] = 0;
-    for (int b = 0; b < 3; b++) {
-        while (k < nu && units[k].n > lim[b]) k++;
+    for (int b = 0; b < 5; b++) {
+        while (k < nu && unit_bucket(units[k]) <= b) k++;
         bucket_first[b + 1] = k;
     }
-    bucket_first[4] = nu;
     for (auto &u : units) {
         u.ring_off = ring_acc;
-        ring_acc += unit_ring_elems(u.n, u.stride);
+        ring_acc += unit_ring_elems(u.stride);
         max_n = std::max(max_n, u.n);
     }
     return ring_acc;
@@ -435,7 +455,7 @@ size_t locus_bytes(int n, int L)
     LocusDesc d{};
     const unsigned long long be = shape_locus(d, n, L);
     const size_t per_tb = (size_t)((std::min(L, n) + 8) & ~3) + (size_t)(std::min(L, n) / 4 + 16) * 8 + 64;
-    return (size_t)be * 13 + (size_t)(d.tile_last + 1) * unit_ring_elems(std::min(n, d.tile_last ? MF_TILE_LEN : n), d.stride) * 4 +
+    return (size_t)be * 13 + (size_t)(d.tile_last + 1) * unit_ring_elems(d.stride) * 4 +
            (size_t)(d.tile_last + 2) * sizeof(LocusDesc) + (size_t)n * 16 + (size_t)(n / 8 + 2) * per_tb + 4096;
 }
 
@@ -644,8 +664,8 @@ struct DevicePipeline {
         CK(launch_prepare(raw_dev, dl, nl, P.seq_acc, Ln.codes.as<unsigned char>(), Ln.F.as<int>(), lo));
         CK(cudaEventRecord(Ln.ev[2], lo));
         FillLaunch fa{Ln.units.as<LocusDesc>(), nu, P.max_n, Ln.codes.as<unsigned char>(), Ln.C.as<int>(), Ln.M.as<int>(), Ln.ring.as<int>(),
-                      Ln.Ib.as<unsigned char>(), Ln.Mp.as<unsigned int>(), D.dP, {0, 0, 0, 0, 0}, Ln.fillflags.as<int>(), J.force_wide ? 1 : 0, env_opts()};
-        for (int b = 0; b < 5; b++) fa.bucket_first[b] = P.bucket_first[b];
+                      Ln.Ib.as<unsigned char>(), Ln.Mp.as<unsigned int>(), D.dP, {0, 0, 0, 0, 0, 0}, Ln.fillflags.as<int>(), J.force_wide ? 1 : 0, env_opts()};
+        for (int b = 0; b < 6; b++) fa.bucket_first[b] = P.bucket_first[b];
         static const bool no_side = getenv("MIRFOLD_NO_SIDE_STREAM") != nullptr;   // A/B runs
         CK(launch_fill(fa, lo, no_side ? nullptr : Ln.side, Ln.ev[10], Ln.ev[11]));
         CK(cudaEventRecord(Ln.ev[3], lo));
@@ -654,7 +674,7 @@ struct DevicePipeline {
         CK(launch_f3(dl, nl, P.n_long, P.max_Ls, Ln.codes.as<unsigned char>(), Ln.C.as<int>(), Ln.F.as<int>(), D.dP, hi));
         {   // kernels launched so far: k_prepare, the fill kernels (16-bit + 32-bit redo per non-empty bucket, generic), k_f3 / k_f3_cta
             int nfill = P.bucket_first[1] > P.bucket_first[0] ? 1 : 0;
-            for (int b = 1; b < 4; b++) if (P.bucket_first[b + 1] > P.bucket_first[b]) nfill += J.force_wide ? 1 : 2;
+            for (int b = 1; b < 5; b++) if (P.bucket_first[b + 1] > P.bucket_first[b]) nfill += J.force_wide ? 1 : 2;
             out.st.kernel_launches += 1 + nfill + (P.n_long > 0 ? 1 : 0) + (P.n_long < nl ? 1 : 0);
         }
         CK(cudaEventRecord(Ln.ev[4], hi));
@@ -1435,6 +1455,21 @@ int mirfold_plan_shards(const uint64_t *seq_off, uint32_t nseq, int span_L, int 
     return MIRFOLD_OK;
 }
 
+int mirfold_plan_fill_units(uint32_t n, int span_L, mirfold_fill_plan *out)
+{
+    if (!out || n < 1 || n > 0x7fffffffu || span_L < 5) return MIRFOLD_ERR_ARG;
+    LocusDesc d{};
+    const unsigned long long be = shape_locus(d, (int)n, span_L);
+    out->kernel = is_bucket_stride(d.stride) ? d.stride : 0;
+    out->stride = d.stride;
+    out->tile_len = d.tile_last ? d.stride : (int)n;
+    out->tile_step = d.tile_last ? d.tile_step : (int)n;
+    out->n_units = d.dmax >= 4 ? d.tile_last + 1 : 0;   // n < 5: nothing to fill
+    out->dmax = d.dmax;
+    out->band_cells = be;
+    return MIRFOLD_OK;
+}
+
 void mirfold_free_result(mirfold_result *res)
 {
     if (!res) return;
@@ -1470,7 +1505,7 @@ int mirfold_debug_matrices(mirfold_ctx *ctx, const char *seq, uint32_t n, int sp
     LocusDesc d{};
     const unsigned long long cells = shape_locus(d, (int)n, span_L);
     std::vector<LocusDesc> units;
-    int bucket_first[5], max_n = 0;
+    int bucket_first[6], max_n = 0;
     const unsigned long long ring_elems = build_fill_units(&d, 1, units, bucket_first, max_n);
     const int nu = (int)units.size();
     CK(Ln.raw.ensure(n)); CK(Ln.loci.ensure(sizeof d)); CK(Ln.codes.ensure(n + 3)); CK(Ln.F.ensure((n + 3) * 4));
@@ -1485,9 +1520,9 @@ int mirfold_debug_matrices(mirfold_ctx *ctx, const char *seq, uint32_t n, int sp
     CK(Ln.fillflags.ensure((size_t)nu * 4 + 4));
     CK(cudaMemsetAsync(Ln.fillflags.p, 0, (size_t)nu * 4 + 4, st));
     FillLaunch fa{Ln.units.as<LocusDesc>(), nu, max_n, Ln.codes.as<unsigned char>(), Ln.C.as<int>(), Ln.M.as<int>(), Ln.ring.as<int>(),
-                  Ln.Ib.as<unsigned char>(), Ln.Mp.as<unsigned int>(), D.dP, {0, 0, 0, 0, 0}, Ln.fillflags.as<int>(),
+                  Ln.Ib.as<unsigned char>(), Ln.Mp.as<unsigned int>(), D.dP, {0, 0, 0, 0, 0, 0}, Ln.fillflags.as<int>(),
                   ((flags & MIRFOLD_FLAG_WIDE) || span_L > MF16_MAX_SPAN) ? 1 : 0, env_opts()};
-    for (int b = 0; b < 5; b++) fa.bucket_first[b] = bucket_first[b];
+    for (int b = 0; b < 6; b++) fa.bucket_first[b] = bucket_first[b];
     CK(launch_fill(fa, st));
     CK(launch_f3(dl, 1, d.n > MF_TILE_LEN ? 1 : 0, d.Ls, Ln.codes.as<unsigned char>(), Ln.C.as<int>(), Ln.F.as<int>(), D.dP, st));
     std::vector<int> hc(cells), hm(cells), hf(n + 3);
@@ -1503,8 +1538,8 @@ int mirfold_debug_matrices(mirfold_ctx *ctx, const char *seq, uint32_t n, int sp
             unsigned long long base = (unsigned long long)(i - 1);
             if (d.tile_last) {
                 const int t = std::min((i - 1) / d.tile_step, d.tile_last);
-                const int a = std::min(t * d.tile_step, (int)n - MF_TILE_LEN);
-                base = (unsigned long long)t * band_elems(MF_TILE_LEN, d.dmax) + (unsigned long long)(i - 1 - a);
+                const int a = std::min(t * d.tile_step, (int)n - d.stride);
+                base = (unsigned long long)t * band_elems(d.stride, d.dmax) + (unsigned long long)(i - 1 - a);
             }
             c[(size_t)i * W + dd] = hc[base + band_doff(d.stride, dd)];
             m[(size_t)i * W + dd] = hm[base + band_doff(d.stride, dd)];

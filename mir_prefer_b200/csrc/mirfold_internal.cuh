@@ -75,16 +75,17 @@ struct LocusDesc {
     int dmax;    // min(Ls, n-1)
     int rec;     // input record index
     int stride;  // band row stride (elements per diagonal)
-    // Long loci (n > MF_TILE_LEN) are filled as overlapping tiles of MF_TILE_LEN bases by the
-    // shared-memory kernels: tile t covers bases a_t+1 .. a_t+MF_TILE_LEN, a_t = min(t*tile_step,
-    // n-MF_TILE_LEN), tile_step = MF_TILE_LEN - dmax.  Every cell value only depends on the bases
-    // inside [i,j], so a tile's cells are the locus' cells; row i is read from its owner tile
+    // Long loci are filled as overlapping tiles of TL bases by the shared-memory kernels (TL = MF_TILE_LEN,
+    // or MF_TILE_LEN_BIG for wide spans: shape_locus() in host.cu; a tiled locus has stride == TL): tile t covers
+    // bases a_t+1 .. a_t+TL, a_t = min(t*tile_step, n-TL), tile_step = TL - dmax.  Every cell value only depends
+    // on the bases inside [i,j], so a tile's cells are the locus' cells; row i is read from its owner tile
     // min((i-1)/tile_step, tile_last), which holds all of (i, i+4..i+dmax).  Untiled: tile_last = 0.
     int tile_last;           // number of tiles - 1
     int tile_step;           // rows owned per tile
     unsigned int tile_rcp;   // ceil(2^32 / tile_step): (i-1)/tile_step == __umulhi(i-1, tile_rcp)
 };
 #define MF_TILE_LEN 608
+#define MF_TILE_LEN_BIG 864   /* the largest shared-memory bucket: one 1024-thread CTA per SM (155 KB of rings) */
 
 // element offset (relative to the locus' band_off) of row i's owner-tile origin, i.e. of cell
 // (i, i+4); cell (i, i+d) sits (d-4)*stride further.  Any cell (i', j') with i <= i' and
@@ -93,8 +94,8 @@ __device__ __forceinline__ unsigned long long band_row_base(const LocusDesc &L, 
 {
     if (L.tile_last == 0) return (unsigned long long)(i - 1);
     const int t = min((int)__umulhi((unsigned)(i - 1), L.tile_rcp), L.tile_last);
-    const int a = min(t * L.tile_step, L.n - MF_TILE_LEN);
-    return (unsigned long long)t * ((unsigned long long)(L.dmax - 3) * MF_TILE_LEN) + (unsigned long long)(i - 1 - a);
+    const int a = min(t * L.tile_step, L.n - L.stride);   // tiled: stride == tile length
+    return (unsigned long long)t * ((unsigned long long)(L.dmax - 3) * L.stride) + (unsigned long long)(i - 1 - a);
 }
 
 // offset of diagonal d inside a locus' band (elements)
@@ -103,13 +104,19 @@ __host__ __device__ __forceinline__ unsigned long long band_elems(int stride, in
 {
     return dmax >= 4 ? (unsigned long long)(dmax - 3) * (unsigned long long)stride : 0ULL;
 }
-// length buckets of the shared-memory fill kernel; longer loci use the generic kernel
-__host__ __device__ __forceinline__ int band_stride_for(int n)
+// length buckets of the shared-memory fill kernels; a stride that is none of them marks a unit of the generic kernel
+__host__ __device__ __forceinline__ bool is_bucket_stride(int stride)
+{
+    return stride == 160 || stride == 352 || stride == MF_TILE_LEN || stride == MF_TILE_LEN_BIG;
+}
+__host__ __device__ __forceinline__ int band_stride_for(int n, bool big)
 {
     if (n <= 160) return 160;
     if (n <= 352) return 352;
-    if (n <= 608) return 608;
-    return (n + 31) & ~31;
+    if (n <= MF_TILE_LEN) return MF_TILE_LEN;
+    if (big && n <= MF_TILE_LEN_BIG) return MF_TILE_LEN_BIG;
+    const int s = (n + 31) & ~31;
+    return is_bucket_stride(s) ? s + 32 : s;   // generic kernel
 }
 
 #define MF_RING_CM 64  /* generic kernel: Cm window ring in global memory (needs >= 33 diagonals) */
@@ -126,7 +133,7 @@ struct FillLaunch {
     unsigned char *Ib;    // one byte per band cell: "some two-loop candidate reproduces c(i,j)" (traceback hint; all ones from the wide kernels)
     unsigned int *Mp;     // narrow kernel: fML as 16-bit row pairs (locus at band_off; layout by bucket, see dev_store_fml16)
     const DevParams *P;
-    int bucket_first[5];  // loci sorted by descending n: [generic | <=608 | <=352 | <=160 | end)
+    int bucket_first[6];  // fill units sorted by (bucket, descending n): [generic | 864 | 608 | 352 | 160 | end)
     int *flags;           // per locus: 1 = the 16-bit kernel left its range, redo with the 32-bit kernel
     int force_wide;       // skip the 16-bit kernel (MIRFOLD_FLAG_WIDE)
     int opts;             // experiment switches (env MIRFOLD_OPTS): bit 0 = no L1 prefetch in the 32-bit DML strips, bit 1 = 32-bit DML strips in the narrow kernels

@@ -52,8 +52,9 @@ cudaError_t launch_plan(const TraceBuffers &b, cudaStream_t st)
 __device__ __noinline__ unsigned long long tb_tiled_off(int i, int d, unsigned int tile_rcp, int tile_last, int tile_step, int n, int dmax)
 {
     const int t = min((int)__umulhi((unsigned)(i - 1), tile_rcp), tile_last);
-    const int a = min(t * tile_step, n - MF_TILE_LEN);
-    return (unsigned long long)t * ((unsigned long long)(dmax - 3) * MF_TILE_LEN) + (unsigned)((d - 4) * MF_TILE_LEN + (i - 1 - a));
+    const int TL = tile_step + dmax;   // tile length == the locus' band stride (608 or 864)
+    const int a = min(t * tile_step, n - TL);
+    return (unsigned long long)t * ((unsigned long long)(dmax - 3) * TL) + (unsigned)((d - 4) * TL + (i - 1 - a));
 }
 
 struct Fold {

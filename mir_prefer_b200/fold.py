@@ -307,6 +307,17 @@ def plan_shards(lengths, span, n_shards):
     return shard_of, cells
 
 
+def plan_fill_units(n, span):
+    """How the band fill cuts a locus of n bases at this span into fill units (mirfold_plan_fill_units; host-only).
+    Returns a dict: kernel (0 = generic, else the bucket stride), stride, tile_len, tile_step, n_units, dmax, band_cells."""
+    lib = _lib.load()
+    fp = _lib.FillPlan()
+    rc = lib.mirfold_plan_fill_units(int(n), int(span), C.byref(fp))
+    if rc != 0:
+        raise MirfoldError(rc, lib.mirfold_strerror(rc).decode())
+    return {k: int(getattr(fp, k)) for k, _ in _lib.FillPlan._fields_}
+
+
 class MirFold:
     """A libmirfold context (one per process; `devices` = CUDA ordinals, default current device)."""
 

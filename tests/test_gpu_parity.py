@@ -129,17 +129,19 @@ def test_long_loci(mf, oracle):
 
 
 def test_tiled_long_loci_edges(mf, oracle):
-    """Loci longer than the largest shared-memory bucket are filled as overlapping 608-nt tiles
+    """Loci longer than 608 nt are filled as overlapping 608-nt tiles at spans < 400
     (LocusDesc::tile_*): lengths around every tile-count boundary for L=300 (step 308), and other
-    spans (step 608-L), cell for cell and hit for hit."""
+    spans (step 608-L; 864-nt tiles from L=400 on, test_big_tile_bucket_edges), cell for cell and hit for hit."""
     lens = [609, 610, 915, 916, 917, 1223, 1224, 1225, 1533, 2500]
     seqs = [synth_loci(400 + n, 1, (n, n))[0] for n in lens]
     st = assert_same(mf, oracle, seqs, 300)
-    assert st["fill_units"] == sum((n - 608 + 307) // 308 + 1 for n in lens)
+    from mir_prefer_b200.fold import plan_fill_units
+    assert st["fill_units"] == sum(plan_fill_units(n, 300)["n_units"] for n in lens)
+    assert plan_fill_units(2500, 300)["n_units"] == ((2500 - 608 + 307) // 308 + 1 if plan_fill_units(2500, 300)["kernel"] == 608 else (2500 - 864 + 563) // 564 + 1)
     assert_same(mf, oracle, seqs[:6], 150)
     assert_same(mf, oracle, seqs[:4], 500)
-    assert_same(mf, oracle, seqs[:3], 544)     # last tiled span (64 owned rows per tile)
-    assert_same(mf, oracle, seqs[:2], 545)     # first span that uses the generic kernel again
+    assert_same(mf, oracle, seqs[:3], 544)     # 864-nt tiles (the last span a 608-nt tile could hold)
+    assert_same(mf, oracle, seqs[:2], 545)
     for L in (5, 9, 31, 40):                   # f3 CTA kernel windows at tiny spans
         assert_same(mf, oracle, seqs[:2], L)
     for s, L in ((seqs[3], 300), (seqs[5], 150), (seqs[1], 500)):
@@ -151,6 +153,33 @@ def test_tiled_long_loci_edges(mf, oracle):
     # a long GC helix leaves the 16-bit range inside some tiles only: those tiles are redone wide
     s = synth_loci(77, 1, (400, 400))[0] + "GC" * 160 + synth_loci(78, 1, (500, 500))[0]
     assert_same(mf, oracle, [s], 300)
+
+
+def test_big_tile_bucket_edges(mf, oracle):
+    """Spans >= 400 put loci longer than 608 nt into the stride-864 bucket (one 1024-thread CTA per unit): a single unit up
+    to 864 nt, overlapping 864-nt tiles beyond (step 864-L).  Lengths around every tile-count boundary for L=500 (step 364),
+    the last tiled span (L=800: 64 owned rows per tile), the first span at which longer loci use the generic kernel again
+    (L=801, while loci <= 864 nt stay in the bucket with diagonals up to n-1), cell for cell and hit for hit."""
+    from mir_prefer_b200.fold import plan_fill_units
+    lens = [864, 865, 1228, 1229, 1593]
+    seqs = [synth_loci(900 + n, 1, (n, n))[0] for n in lens]
+    st = assert_same(mf, oracle, seqs, 500)
+    plans = [plan_fill_units(n, 500) for n in lens]
+    assert [p["n_units"] for p in plans] == [1, 2, 2, 3, 4] and all(p["kernel"] == 864 for p in plans)
+    assert st["fill_units"] == 12
+    assert_same(mf, oracle, [seqs[1], seqs[3]], 800)
+    assert plan_fill_units(1229, 800)["n_units"] == 7
+    assert_same(mf, oracle, [seqs[0], seqs[1] + "A"], 801)
+    assert plan_fill_units(864, 801)["kernel"] == 864 and plan_fill_units(866, 801)["kernel"] == 0
+    for s, L in ((seqs[3], 500), (seqs[0], 801)):
+        o = oracle.fold(s, L, matrices=True)
+        c, m, f3 = mf.debug_matrices(s, L)
+        assert (o["c"] == c).all()
+        assert (np.minimum(o["m"], 1000000) == np.minimum(m, 1000000)).all()
+        assert (o["f3"][:len(s) + 3] == f3[:len(s) + 3]).all()
+    # a long GC helix leaves the 16-bit range inside one 864-nt tile only: that tile is redone by the 32-bit kernel
+    s = synth_loci(77, 1, (500, 500))[0] + "GC" * 170 + synth_loci(78, 1, (600, 600))[0]
+    assert_same(mf, oracle, [s], 500)
 
 
 def test_randomized_lengths_and_spans(mf, oracle):

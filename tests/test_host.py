@@ -67,3 +67,43 @@ def test_plan_shards_rejects_bad_arguments():
     off = np.array([0, 10, 15], np.uint64)
     assert lib.mirfold_plan_shards(off.ctypes.data_as(C.POINTER(C.c_uint64)), 2, 300, 0, None, None) == -3
     assert lib.mirfold_plan_shards(off.ctypes.data_as(C.POINTER(C.c_uint64)), 2, 300, 2, None, None) == 0
+
+
+def test_fill_units_tile_every_row_of_every_locus():
+    """mirfold_plan_fill_units (the shape the band fill itself uses): buckets by length, 608-nt tiles for long loci at
+    narrow spans, 864-nt tiles (and single 864 units for 609..864 nt) at wide spans, the generic kernel only where no
+    tile would own 64 rows.  For every tiled locus: every row i has an owner tile that contains all of (i, i+4..i+dmax),
+    owner tiles change exactly at multiples of tile_step, and the last tile ends at base n."""
+    from mir_prefer_b200.fold import plan_fill_units
+    BIG = 400   # spans from here on use the 864 bucket (host.cu: MF_BIG_TILE_MIN_SPAN)
+    for L in (5, 30, 150, 300, 399, 400, 500, 544, 545, 700, 800, 801, 1000):
+        for n in (5, 6, 160, 161, 352, 353, 608, 609, 700, 864, 865, 866, 927, 928, 929, 1228, 1229, 1500, 2500, 5000, 10000):
+            p = plan_fill_units(n, L)
+            dmax = min(L, n - 1)
+            assert p["dmax"] == dmax
+            if n <= 608:
+                assert p["kernel"] == p["stride"] == (160 if n <= 160 else 352 if n <= 352 else 608)
+                assert p["n_units"] == (1 if dmax >= 4 else 0) and p["tile_len"] == n
+                continue
+            big = dmax >= BIG and (n <= 864 or 864 - dmax >= 64)
+            if big and n <= 864:
+                assert (p["kernel"], p["stride"], p["n_units"], p["tile_len"]) == (864, 864, 1, n), (n, L, p)
+                continue
+            TL = 864 if big else 608
+            if TL - dmax < 64:
+                assert p["kernel"] == 0 and p["n_units"] == 1 and p["stride"] >= n and p["stride"] % 32 == 0, (n, L, p)
+                assert p["stride"] not in (160, 352, 608, 864)
+                continue
+            S = TL - dmax
+            assert (p["kernel"], p["stride"], p["tile_len"], p["tile_step"]) == (TL, TL, TL, S), (n, L, p)
+            nt = p["n_units"]
+            assert nt == (n - TL + S - 1) // S + 1 and nt >= 2
+            assert p["band_cells"] == nt * TL * (dmax - 3)
+            starts = [min(t * S, n - TL) for t in range(nt)]
+            assert starts[-1] == n - TL
+            for i in list(range(1, min(n - 4, 3 * S) + 1)) + list(range(max(1, n - 2 * TL), n - 3)):
+                t = min((i - 1) // S, nt - 1)
+                a = starts[t]
+                assert a + 1 <= i, (n, L, i)
+                assert min(i + dmax, n) <= a + TL, (n, L, i)
+    assert plan_fill_units(4, 300)["n_units"] == 0
