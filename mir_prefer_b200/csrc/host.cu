@@ -367,13 +367,15 @@ cudaError_t exclusive_scan(Lane &Ln, const unsigned long long *in, unsigned long
 
 // Band shape of one locus: stride bucket or, for a longer locus with a span that leaves at least
 // MF_TILE_MIN_STEP owned rows per tile, overlapping tiles for the shared-memory kernels.  A tile owns TL - dmax of
-// its TL rows, so wide spans (dmax >= big_tile_min_span(), and every span the 608-nt tile cannot hold) use the
-// 864 bucket: at L = 500 a 608-nt tile owns 108 rows (the locus' cells are computed 3.3 times over), an 864-nt
-// tile 364 (1.4 times); loci of 609..864 nt are then one untiled unit of that bucket.
+// its TL rows, so spans from big_tile_min_span() on use the 864 bucket: at L = 500 a 608-nt tile owns 108 rows (the
+// locus' cells are computed 3.3 times over), an 864-nt tile 364 (1.7 times); at L = 300 it is 1.49 against 1.27.  Loci
+// of 609..864 nt are then one untiled unit of that bucket.  The 864 kernel is one CTA per SM and 13 % (L = 300) to
+// 35 % (L = 500) slower per executed cell than the 608 kernel (two CTAs per SM hide each other's barriers), so narrower
+// spans keep the 608-nt tiles.  Measured same-box (profiles/r02_v7_bigtile_ab.txt): long loci -6.6 % at L = 300, -29 % at L = 500.
 // Returns the band elements (per int32 array) the locus occupies.
 #define MF_TILE_MIN_STEP 64
 #ifndef MF_BIG_TILE_MIN_SPAN
-#define MF_BIG_TILE_MIN_SPAN 400
+#define MF_BIG_TILE_MIN_SPAN 300
 #endif
 static int big_tile_min_span()
 {

@@ -129,22 +129,25 @@ def test_long_loci(mf, oracle):
 
 
 def test_tiled_long_loci_edges(mf, oracle):
-    """Loci longer than 608 nt are filled as overlapping 608-nt tiles at spans < 400
-    (LocusDesc::tile_*): lengths around every tile-count boundary for L=300 (step 308), and other
-    spans (step 608-L; 864-nt tiles from L=400 on, test_big_tile_bucket_edges), cell for cell and hit for hit."""
-    lens = [609, 610, 915, 916, 917, 1223, 1224, 1225, 1533, 2500]
+    """Loci longer than 608 nt are filled as overlapping tiles (LocusDesc::tile_*): 608-nt tiles at spans < 300 (step
+    608-L), 864-nt tiles from L=300 on (step 864-L; more in test_big_tile_bucket_edges).  Lengths around every tile-count
+    boundary of both at L=299 (step 309) and L=300 (step 564), and other spans, cell for cell and hit for hit."""
+    from mir_prefer_b200.fold import plan_fill_units
+    lens = [609, 610, 864, 865, 917, 918, 1226, 1227, 1428, 1429, 2500]
     seqs = [synth_loci(400 + n, 1, (n, n))[0] for n in lens]
     st = assert_same(mf, oracle, seqs, 300)
-    from mir_prefer_b200.fold import plan_fill_units
-    assert st["fill_units"] == sum(plan_fill_units(n, 300)["n_units"] for n in lens)
-    assert plan_fill_units(2500, 300)["n_units"] == ((2500 - 608 + 307) // 308 + 1 if plan_fill_units(2500, 300)["kernel"] == 608 else (2500 - 864 + 563) // 564 + 1)
+    assert [plan_fill_units(n, 300)["n_units"] for n in lens] == [1, 1, 1, 2, 2, 2, 2, 2, 2, 3, 4]
+    assert st["fill_units"] == 22
+    st = assert_same(mf, oracle, seqs, 299)
+    assert [plan_fill_units(n, 299)["n_units"] for n in lens] == [2, 2, 2, 2, 2, 3, 3, 4, 4, 4, 8]
+    assert st["fill_units"] == 36
     assert_same(mf, oracle, seqs[:6], 150)
     assert_same(mf, oracle, seqs[:4], 500)
-    assert_same(mf, oracle, seqs[:3], 544)     # 864-nt tiles (the last span a 608-nt tile could hold)
+    assert_same(mf, oracle, seqs[3:6], 544)    # 864-nt tiles (the last span a 608-nt tile could hold)
     assert_same(mf, oracle, seqs[:2], 545)
     for L in (5, 9, 31, 40):                   # f3 CTA kernel windows at tiny spans
         assert_same(mf, oracle, seqs[:2], L)
-    for s, L in ((seqs[3], 300), (seqs[5], 150), (seqs[1], 500)):
+    for s, L in ((seqs[3], 300), (seqs[5], 150), (seqs[1], 500), (seqs[6], 299)):
         o = oracle.fold(s, L, matrices=True)
         c, m, f3 = mf.debug_matrices(s, L)
         assert (o["c"] == c).all()
@@ -156,7 +159,7 @@ def test_tiled_long_loci_edges(mf, oracle):
 
 
 def test_big_tile_bucket_edges(mf, oracle):
-    """Spans >= 400 put loci longer than 608 nt into the stride-864 bucket (one 1024-thread CTA per unit): a single unit up
+    """Spans >= 300 put loci longer than 608 nt into the stride-864 bucket (one 1024-thread CTA per unit): a single unit up
     to 864 nt, overlapping 864-nt tiles beyond (step 864-L).  Lengths around every tile-count boundary for L=500 (step 364),
     the last tiled span (L=800: 64 owned rows per tile), the first span at which longer loci use the generic kernel again
     (L=801, while loci <= 864 nt stay in the bucket with diagonals up to n-1), cell for cell and hit for hit."""

@@ -75,8 +75,8 @@ def test_fill_units_tile_every_row_of_every_locus():
     tile would own 64 rows.  For every tiled locus: every row i has an owner tile that contains all of (i, i+4..i+dmax),
     owner tiles change exactly at multiples of tile_step, and the last tile ends at base n."""
     from mir_prefer_b200.fold import plan_fill_units
-    BIG = 400   # spans from here on use the 864 bucket (host.cu: MF_BIG_TILE_MIN_SPAN)
-    for L in (5, 30, 150, 300, 399, 400, 500, 544, 545, 700, 800, 801, 1000):
+    BIG = 300   # spans from here on use the 864 bucket (host.cu: MF_BIG_TILE_MIN_SPAN)
+    for L in (5, 30, 150, 299, 300, 400, 500, 544, 545, 700, 800, 801, 1000):
         for n in (5, 6, 160, 161, 352, 353, 608, 609, 700, 864, 865, 866, 927, 928, 929, 1228, 1229, 1500, 2500, 5000, 10000):
             p = plan_fill_units(n, L)
             dmax = min(L, n - 1)
