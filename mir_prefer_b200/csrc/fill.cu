@@ -129,7 +129,9 @@ __device__ __forceinline__ int dev_fml(const DevParams *__restrict__ P, const un
 
 // phase A: DML for the strip d..d1 from fML diagonals <= d-1.  One (row, part) per thread; `part`
 // splits the e-range when the strip has fewer rows than the CTA has threads.
-template <int NT, class StrideT>
+// STORE_INF: a (row, diagonal) without a valid split is written as MF_INF when the thread is its only writer, so the
+// ring rows need no preset (k_fill_s16 switching to these strips mid-locus); the default leaves such cells untouched.
+template <int NT, bool STORE_INF = false, class StrideT>
 __device__ __forceinline__ void dev_phase_a(const int *Mb, int *rD, StrideT NS, int n, int d,
                                             int d1, int tid, bool prefetch = true)
 {
@@ -189,7 +191,7 @@ __device__ __forceinline__ void dev_phase_a(const int *Mb, int *rD, StrideT NS, 
         }
 #pragma unroll
         for (int s = 0; s < 5; s++)
-            if (s < ns && acc[s] < MF_INF) {
+            if (s < ns && (acc[s] < MF_INF || (STORE_INF && nparts == 1))) {
                 int *dst = &rD[((d + s) & (MF_RING_DML - 1)) * NS + (i - 1)];
                 if (nparts == 1) *dst = acc[s];
                 else atomicMin(dst, acc[s]);
@@ -891,11 +893,17 @@ __global__ void __launch_bounds__(NT, MINB) k_fill_s16(FillLaunch a)
     unsigned char *sS = (unsigned char *)(sMk + 2 * MF16_NMK * 32);   // [NS+8]
     unsigned char *sS1 = sS + NS + 8;
     unsigned char *sPair = sS1 + NS + 8;                      // [64]
+    int *sWideM = (int *)(sPair + 64);                        // [1] DYNW buckets: some fML left the 16-bit strips' range
     __shared__ int sCount[3];
     __shared__ int sFlag;
     __shared__ int sRowP[32];                                 // ring row (words) of pair slot pp at [pp & 31]
     const RingRows rr{sRowP, RS};
 
+    // Buckets whose windows are long enough for fML to drop below MF16M_GUARD on ordinary sequence (-136 kcal/mol: about
+    // half of all 500-nt windows at GC 0.40) do not hand such a unit to the 32-bit kernel: from the first out-of-range fML
+    // on, the DML strips -- the only consumer of the 16-bit fML copy -- read the int32 band instead, and the interior-loop
+    // rings stay 16-bit.  Only c below MF16_GUARD (-320 kcal/mol) still flags the unit.
+    constexpr bool DYNW = NS > 352;
     const LocusDesc L = a.loci[blockIdx.x];
     const int n = L.n, Ls = L.Ls, dmax = L.dmax;
     const DevParams *__restrict__ P = a.P;
@@ -913,6 +921,7 @@ __global__ void __launch_bounds__(NT, MINB) k_fill_s16(FillLaunch a)
     if (tid < 64) sPair[tid] = P->pair[tid];
     if (tid < 3) sCount[tid] = 0;
     if (tid == 0) sFlag = 0;
+    if (DYNW && tid == 0) *sWideM = 0;
     for (int k = tid; k < 2 * MF16_NQ * 32; k += NT) sCst[k] = (&P->s16_cst[0][0][0])[k];
     for (int k = tid; k < 2 * MF16_NMK * 32; k += NT) sMk[k] = (&P->s16_mk[0][0][0])[k];
 
@@ -951,9 +960,20 @@ __global__ void __launch_bounds__(NT, MINB) k_fill_s16(FillLaunch a)
 
     TL_DECL
     for (int it = 4; it <= dmax + 1; it++) {
+        bool newest_row_stored = false;
         if (it >= 5 && (it - 5) % 5 == 0 && it - 1 <= dmax) {
             // DML strip [it-1, it+3]
-            if (a.opts & 2) dev_phase_a<NT>(Mb, rD, NS, n, it - 1, min(it + 3, dmax), tid, !(a.opts & 1));
+            if (DYNW && *(volatile int *)sWideM) {   // uniform: written before the barrier that ended the last iteration
+                if (BULK) {   // the int32 fML row of diagonal it-2 is still only in the shared row buffer
+                    if (tid == CT && it - 2 >= 4) {
+                        dev_bulk_store_row(Mb + (it - 6) * NS, sMrow + (it & 1) * NS, (unsigned)(((n - it + 2) * 4 + 15) & ~15));
+                        dev_bulk_wait_all();
+                    }
+                    newest_row_stored = true;
+                    __syncthreads();
+                }
+                dev_phase_a<NT, true>(Mb, rD, NS, n, it - 1, min(it + 3, dmax), tid, !(a.opts & 1));
+            } else if (a.opts & 2) dev_phase_a<NT>(Mb, rD, NS, n, it - 1, min(it + 3, dmax), tid, !(a.opts & 1));
             else if (OC && (a.opts & 4)) dev_phase_a16<NT>(Mp, rD, NS, n, it - 1, min(it + 3, dmax), tid, !(a.opts & 1));
             else dev_phase_a16_sel<NT, OC>(Mp, rD, NS, n, it - 1, min(it + 3, dmax), tid);
             TL_MARK(0)
@@ -1040,7 +1060,7 @@ __global__ void __launch_bounds__(NT, MINB) k_fill_s16(FillLaunch a)
             const int mt = tid - CT;
             const int dm = it - 1;
             // the int32 fML row of diagonal it-2 (complete since the last barrier) leaves through the TMA engine
-            if (BULK && mt == 0 && dm - 1 >= 4)
+            if (BULK && mt == 0 && dm - 1 >= 4 && !newest_row_stored)
                 dev_bulk_store_row(Mb + (dm - 5) * NS, sMrow + ((dm - 1) & 1) * NS, (unsigned)(((n - dm + 1) * 4 + 15) & ~15));
             if (dm >= 4) {
                 const int *Mprev = sMrow + ((dm - 1) & 1) * NS;
@@ -1049,7 +1069,7 @@ __global__ void __launch_bounds__(NT, MINB) k_fill_s16(FillLaunch a)
                     const int m = dev_fml16(P, sS, sS1, sPair, sB, rr, Mprev, rD, NS, i, dm, Ls);
                     if (!BULK) Mb[(dm - 4) * NS + i - 1] = m;
                     Mcur[i - 1] = m;
-                    dev_store_fml16_sel<OC>(Mp, NS, dm, i, m, &sFlag);   // 16-bit copy (copies) for the DML strips
+                    dev_store_fml16_sel<OC>(Mp, NS, dm, i, m, DYNW ? sWideM : &sFlag);   // 16-bit copy (copies) for the DML strips
                 }
             }
             TL_MARK(1)
