@@ -874,7 +874,7 @@ __device__ __forceinline__ int dev_fml16(const DevParams *__restrict__ P, const 
 #define TL_MARK(k)
 #define TL_DUMP
 #endif
-template <int NS, int NT, int NWM, int MINB>
+template <int NS, int NT, int NWM, int MINB, bool DYNW>
 __global__ void __launch_bounds__(NT, MINB) k_fill_s16(FillLaunch a)
 {
     constexpr int RS = Fill16Smem<NS>::RS, RW = Fill16Smem<NS>::ring_words;
@@ -899,11 +899,12 @@ __global__ void __launch_bounds__(NT, MINB) k_fill_s16(FillLaunch a)
     __shared__ int sRowP[32];                                 // ring row (words) of pair slot pp at [pp & 31]
     const RingRows rr{sRowP, RS};
 
-    // Buckets whose windows are long enough for fML to drop below MF16M_GUARD on ordinary sequence (-136 kcal/mol: about
-    // half of all 500-nt windows at GC 0.40) do not hand such a unit to the 32-bit kernel: from the first out-of-range fML
-    // on, the DML strips -- the only consumer of the 16-bit fML copy -- read the int32 band instead, and the interior-loop
-    // rings stay 16-bit.  Only c below MF16_GUARD (-320 kcal/mol) still flags the unit.
-    constexpr bool DYNW = NS > 352;
+    // DYNW (launched for spans >= MF_DYNW_MIN_SPAN, launch_fill_bucket): windows long enough for fML to drop below
+    // MF16M_GUARD on ordinary sequence (-136 kcal/mol: about half of all 500-nt windows at GC 0.40) do not hand the unit
+    // to the 32-bit kernel: from the first out-of-range fML on, the DML strips -- the only consumer of the 16-bit fML
+    // copy -- read the int32 band instead, and the interior-loop rings stay 16-bit.  Only c below MF16_GUARD (-320
+    // kcal/mol) still flags the unit.  The switch costs the stride-864 kernel 4 % where it never fires (L = 300: 172.4 ->
+    // 180.9 ms on the long-locus law), hence two instantiations.
     const LocusDesc L = a.loci[blockIdx.x];
     const int n = L.n, Ls = L.Ls, dmax = L.dmax;
     const DevParams *__restrict__ P = a.P;
@@ -1228,7 +1229,11 @@ static cudaError_t configure_fill_bucket()
 {
     cudaError_t e = cudaFuncSetAttribute(k_fill_smem<NS, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FillSmem<NS>::bytes);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_fill_s16<NS, NT, MF16_NWM(NT), MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Fill16Smem<NS>::bytes);
+    if (NS > 352) {
+        e = cudaFuncSetAttribute(k_fill_s16<NS, NT, MF16_NWM(NT), MINB, (NS > 352)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Fill16Smem<NS>::bytes);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaFuncSetAttribute(k_fill_s16<NS, NT, MF16_NWM(NT), MINB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Fill16Smem<NS>::bytes);
 }
 // function attributes are per device: called once per device of a context (mirfold_open)
 cudaError_t fill_configure_device()
@@ -1253,7 +1258,9 @@ static cudaError_t launch_fill_bucket(const FillLaunch &a, int first, int count,
     else {
         b.flags = a.flags + first;
         cudaError_t e;
-        k_fill_s16<NS, NT, MF16_NWM(NT), MINB><<<count, NT, smem16, st>>>(b);
+        // wide spans: the instantiation that survives out-of-range fML (FillLaunch::opts bit 3, set by the host from the span)
+        if (NS > 352 && (a.opts & 8)) k_fill_s16<NS, NT, MF16_NWM(NT), MINB, (NS > 352)><<<count, NT, smem16, st>>>(b);
+        else k_fill_s16<NS, NT, MF16_NWM(NT), MINB, false><<<count, NT, smem16, st>>>(b);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }

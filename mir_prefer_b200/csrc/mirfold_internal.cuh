@@ -41,6 +41,7 @@
 #define MF16M_VALID 2700    /* a sum of two finite fML is below this; anything with an INF operand is above */
 #define MF16M_GUARD (-13600)
 #define MF16_MAX_SPAN 1000  /* hairpin extrapolation keeps fML < 1350 up to this span */
+#define MF_DYNW_MIN_SPAN 400  /* spans from here on: fML of ordinary sequence can pass MF16M_GUARD (measured: min fML -13340 at L=400, -16179 at L=500) */
 
 struct DevParams {
     int hairpinE[MF_MAX_SPAN + 2];  // by loop size, incl. the lxc*log extrapolation (A.2)
@@ -136,7 +137,8 @@ struct FillLaunch {
     int bucket_first[6];  // fill units sorted by (bucket, descending n): [generic | 864 | 608 | 352 | 160 | end)
     int *flags;           // per locus: 1 = the 16-bit kernel left its range, redo with the 32-bit kernel
     int force_wide;       // skip the 16-bit kernel (MIRFOLD_FLAG_WIDE)
-    int opts;             // experiment switches (env MIRFOLD_OPTS): bit 0 = no L1 prefetch in the 32-bit DML strips, bit 1 = 32-bit DML strips in the narrow kernels
+    int opts;             // experiment switches (env MIRFOLD_OPTS): bit 0 = no L1 prefetch in the 32-bit DML strips, bit 1 = 32-bit DML strips in the narrow kernels;
+                          // bit 3 (set by the host for spans >= MF_DYNW_MIN_SPAN): launch the 608/864 instantiations that switch to int32 strips on out-of-range fML
 };
 cudaError_t launch_prepare(const char *raw, const LocusDesc *loci, int nloci, unsigned long long total_codes,
                            unsigned char *codes, int *F, cudaStream_t st);
