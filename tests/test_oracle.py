@@ -5,7 +5,7 @@ import os
 
 import pytest
 
-from conftest import GOLDEN, golden_cases
+from conftest import GOLDEN, ROOT, golden_cases
 from mir_prefer_b200.corpus import lcg_records, records_to_fasta
 
 
@@ -42,3 +42,17 @@ def test_oracle_struct_api_matches_text(oracle):
     assert r["hits"] == [(".(((((....)))))", -930, 18), (".(((((....))))).", -980, 9),
                          ("(((((....)))))....(((((....)))))", -2010, 1)]
     assert r["total"] == -2010
+
+
+def test_gpu_mini_check_digests_are_the_oracles():
+    """tools/gpu_mini_check.py compares GPU results with digests computed here on the CPU: they must be the oracle's."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("gpu_mini_check", os.path.join(ROOT, "tools", "gpu_mini_check.py"))
+    mc = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mc)
+    import oracle as O
+    from mir_prefer_b200.corpus import synth_loci
+    O.build()
+    for n, L in mc.CASES[:3]:
+        o = O.fold(synth_loci(700 + n, 1, (n, n))[0], L)
+        assert mc.digest(o["hits"], o["total"]) == mc.WANT[(n, L)], (n, L)
